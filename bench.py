@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the mpv-prescalers hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic frames.  Default workload is
+BASELINE.json configs[1]: ravu-lite-ar-r3 1080p -> 2160p luma, 64-frame batch per GPU.  Prints ONE JSON
+line (rank 0).  ``--impl reference`` times the CPU restatement of the reference (oracle/) on the host
+cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (hook, channels, h, w, frames per GPU, output factor or (oh, ow), BASELINE.json config index)
+    "ravu-lite-ar-r3": ("ravu-lite-ar-r3.hook", 1, 1080, 1920, 64, 2, 1),
+    "ravu-lite-r3-540p": ("ravu-lite-r3.hook", 1, 540, 960, 1, 2, 0),
+    "ravu-r4": ("ravu-r4.hook", 1, 1080, 1920, 64, 2, 2),
+    "ravu-r3-rgb": ("compute/ravu-r3-rgb.hook", 3, 1080, 1920, 16, 2, 2),
+    "ravu-zoom-r3": ("ravu-zoom-r3.hook", 1, 720, 1280, 8, (2160, 3840), 3),
+    "ravu-zoom-ar-r2": ("ravu-zoom-ar-r2.hook", 1, 720, 1280, 8, (2160, 3840), 3),
+    "ravu-3x-r3": ("compute/ravu-3x-r3.hook", 1, 720, 1280, 16, 3, 3),
+    "nnedi3-nns256-win8x6": ("nnedi3-nns256-win8x6.hook", 1, 2160, 3840, 2, 2, 4),
+    "nnedi3-nns32-win8x4": ("nnedi3-nns32-win8x4.hook", 1, 1080, 1920, 8, 2, 4),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nm, val in zip(names, s[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_work(wl, n_frames):
+    """(output Mpix, algorithmic bytes, algorithmic flops) of one step on one GPU."""
+    hook, c, h, w, _, fac, _ = WORKLOADS[wl]
+    oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
+    out_px = n_frames * oh * ow
+    nbytes = 4.0 * c * n_frames * (h * w + oh * ow)
+    flops = 0.0
+    if hook.startswith("nnedi3"):
+        import re
+
+        m = re.search(r"nns(\d+)-win8x(\d)", hook)
+        nns, s = int(m.group(1)), int(m.group(2))
+        flops = 2.0 * (8 * s) * (2 * nns) * (3.0 * h * w) * n_frames
+    return out_px / 1e6, nbytes, flops
+
+
+def cpu_frames(wl, count, seed0=0):
+    import numpy as np
+    from mpv_prescalers_b200.synth import batch
+
+    hook, c, h, w, _, _, cfg = WORKLOADS[wl]
+    x = batch(count, c, h, w, config=cfg + 10 * seed0)
+    return x
+
+
+def _cpu_one(args):
+    """Worker: run the oracle on one frame (executed in a separate process for --impl reference)."""
+    wl, frame = args
+    import numpy as np
+
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from mpv_prescalers_b200 import HookFile, find_hook
+    from oracle import nnedi3_np, ravu_np
+
+    hook, c, h, w, _, fac, _ = WORKLOADS[wl]
+    hk = HookFile.parse(find_hook(hook))
+    v = hk.variant
+    img = frame[0] if c == 1 else np.moveaxis(frame, 0, -1)
+    t0 = time.perf_counter()
+    if v.family == "nnedi3":
+        out, _ = nnedi3_np.nnedi3(img, v)
+    else:
+        osz = None if isinstance(fac, int) else (fac[1], fac[0])
+        out = ravu_np.run(img, v, osz).out
+    return time.perf_counter() - t0, int(out.shape[0] * out.shape[1])
+
+
+def cpu_baseline(wl, budget_s=20.0, procs=1):
+    """Time the oracle (a port of the reference's shader math) on a bounded sample of the workload."""
+    import numpy as np
+
+    hook, c, h, w, _, fac, _ = WORKLOADS[wl]
+    # nnedi3 at 2160p is minutes per frame on a CPU: use a crop of the same planes
+    crop = (270, 480) if hook.startswith("nnedi3") else (h, w)
+    frames = cpu_frames(wl, max(procs, 1))[:, :, : crop[0], : crop[1]]
+    t0 = time.perf_counter()
+    done_px, used = 0, 0
+    if procs <= 1:
+        while True:
+            dt, px = _cpu_one((wl, frames[used % len(frames)]))
+            done_px += px
+            used += 1
+            if time.perf_counter() - t0 > budget_s * 0.5 or used >= 4:
+                break
+        wall = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(_cpu_one, [(wl, frames[i]) for i in range(procs)])  # warm (imports, page-in)
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_one, [(wl, frames[i]) for i in range(procs)])
+            wall = time.perf_counter() - t0
+        done_px, used = sum(r[1] for r in res), procs
+    return {
+        "value": done_px / 1e6 / wall,
+        "unit": "Mpix/s",
+        "cores": procs,
+        "kind": "port",
+        "sample": f"{used} frame(s) of {crop[1]}x{crop[0]} from the same synthetic workload, NumPy fp32 oracle, {procs} process(es)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ravu-lite-ar-r3", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload
+    hook, c, h, w, nf_default, fac, cfg_idx = WORKLOADS[wl]
+    nf = args.frames or nf_default
+    oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
+    config = {
+        "workload": f"{hook} {w}x{h}->{ow}x{oh} {'luma' if c == 1 else '3ch'} fp32, {nf} frames per GPU (BASELINE.json configs[{cfg_idx}])",
+        "frames_per_gpu": nf,
+        "parallelism": f"frame-sharded x{world}, no collective",
+        "l2": "working set per step exceeds the 126 MB L2" if 4.0 * c * nf * (h * w + oh * ow) > 2.5e8 else "L2 flushed between steps",
+    }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = os.cpu_count() or 1
+        base = cpu_baseline(wl, procs=procs)
+        steps = []
+        for _ in range(max(0, args.steps - 1)):
+            steps.append(cpu_baseline(wl, procs=procs)["value"])
+        vals = [base["value"]] + steps
+        val = sum(vals) / len(vals)
+        base["value"] = val
+        line = {
+            "impl": "reference", "metric": "output Mpix/s", "value": val, "unit": "Mpix/s", "n_gpus": 0, "steps": len(vals),
+            "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = NumPy restatement of the reference's GLSL (oracle/), the GLSL itself needs mpv+GL/Vulkan which this image lacks",
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    from mpv_prescalers_b200 import HookFile, _native, find_hook, prescale
+    from mpv_prescalers_b200.api import plan, upload_weights, _launch
+    from mpv_prescalers_b200.sharding import max_over_ranks
+    from mpv_prescalers_b200.synth import torch_batch
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    hk = HookFile.parse(find_hook(hook))
+    out_size = None if isinstance(fac, int) else fac
+    pl = plan(hk, (h, w), out_size)
+    W = upload_weights(hk, local_rank)
+    x = torch_batch(nf, c, h, w, dev, seed=1000 * cfg_idx + rank)
+    lib = _native.lib()
+    flush = None
+    if "flushed" in config["l2"]:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        out, _ = _launch(hk, pl, x, W, False)
+        return out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+        if flush is not None:
+            flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mpvp_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        evs[i][0].record()
+        out = step()
+        evs[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.mpvp_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(kernel_ms)
+    total_ms = max_over_ranks(total_ms, dev)
+    ms_per_step = total_ms / args.steps
+    mpix, abytes, aflops = algorithmic_work(wl, nf)
+    value = mpix * world / (ms_per_step / 1e3)
+
+    hbm_peak, tc_peak, src = peaks()
+    launches_per_step = max(1, launches // max(args.steps, 1))
+    if aflops > 0:
+        ach = aflops / (ms_per_step / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
+                "peak_source": src, "hbm_frac": abytes / (ms_per_step / 1e3) / 1e9 / hbm_peak}
+    else:
+        ach = abytes / (ms_per_step / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": src}
+    roof["kernel"] = f"{pl.family} fused kernel, {launches_per_step} launch(es) per step, avg {ms_per_step / launches_per_step:.4f} ms"
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            with open(tr) as f:
+                roof["traffic"] = json.load(f).get(wl)
+        except Exception:
+            pass
+
+    # ---- end to end: pinned host input -> H2D -> kernel -> D2H, through the public prescale() ----------
+    e2e = None
+    if not args.no_e2e:
+        xh = x.cpu().pin_memory()
+        e2e_steps = max(1, min(args.steps, 3))
+        o = prescale(xh, hk, out_size)  # warm-up (allocations, pinned output pool)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            o = prescale(xh, hk, out_size)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt, dev)
+        e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * 4),
+               "d2h_bytes_per_step": int(o.numel() * 4), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+        del o, xh
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl, procs=1)
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = {
+            "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

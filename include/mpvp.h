@@ -1,0 +1,139 @@
+/*
+ * mpvp.h -- C ABI of libmpvp.so: the B200 (sm_100a) implementation of the mpv-prescalers
+ * per-pixel hot path (RAVU family + NNEDI3).
+ *
+ * The reference has no FFI: its "interface" is the mpv user-shader file, consumed by a host
+ * player that (a) uploads every //!TEXTURE block once at load time and (b) runs each //!DESC pass
+ * per frame at its hook point (reference README.md:33-37).  This header is
+ * that contract restated for a C caller:
+ *
+ *   load time   mpvp_weights_create_lut()      <- //!TEXTURE name / SIZE / FORMAT rgba16f + hex payload
+ *                                                 (ravu-lite-ar-r3.hook:198-202)
+ *               mpvp_weights_create_nnedi3()   <- inline W(i,..)/WS(..) literals
+ *                                                 (nnedi3-nns16-win8x4.hook:31-49)
+ *   per batch   mpvp_ravu_lite_launch()        <- passes "RAVU-Lite(-AR) (step1|step2, rN)"
+ *                                                 (ravu-lite-ar-r3.hook:15-197), fused
+ *               mpvp_ravu_launch()             <- passes "RAVU (step1..4, luma|yuv|rgb, rN)"
+ *                                                 (ravu-r2.hook:15-338, ravu-r2-rgb.hook), fused chain
+ *               mpvp_ravu3x_launch()           <- pass "RAVU-3x (luma|yuv|rgb, rN)"
+ *                                                 (compute/ravu-3x-r2.hook:15-115)
+ *               mpvp_ravu_zoom_launch()        <- pass "RAVU-Zoom(-AR) (luma|yuv|rgb, rN)"
+ *                                                 (ravu-zoom-r2.hook:15-134, ravu-zoom-ar-r2.hook:15-208)
+ *               mpvp_nnedi3_launch()           <- passes "NNEDI3 (double_y|combine_y|double_x|combine_x, ..)"
+ *                                                 (nnedi3-nns16-win8x4.hook:15-194)
+ *
+ * Conventions
+ *   - all frame pointers are DEVICE pointers owned by the caller; planes are float32 in [0,1],
+ *     layout [n][channels][h][w] with explicit strides given in ELEMENTS;
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) on the device that owns the weights; no hidden synchronisation, no allocation;
+ *   - return value 0 = success, negative = error (MPVP_E_*); mpvp_last_error() returns a
+ *     thread-local description of the last failure;
+ *   - `bucket_out` (nullable, int32) receives the LUT row chosen for every key evaluation -- used by
+ *     the parity tests to check the >= 99.99 % bucket-agreement rule.
+ *   - the *_host entry points take HOST pointers (pageable or pinned), stage them through device
+ *     scratch owned by the library, run the same kernels and copy the result back before returning.
+ */
+#ifndef MPVP_H
+#define MPVP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPVP_ABI_VERSION 1
+
+#define MPVP_OK 0
+#define MPVP_E_INVALID (-1)   /* bad argument */
+#define MPVP_E_CUDA (-2)      /* CUDA runtime error (see mpvp_last_error) */
+#define MPVP_E_UNSUPPORTED (-3)
+#define MPVP_E_NOMEM (-4)
+
+typedef struct mpvp_weights mpvp_weights; /* opaque, lives on one device */
+
+/* Key-section constants extracted from the hook text. */
+typedef struct mpvp_key_params {
+  float gauss[36];          /* sigma=2 Gaussian over the inner g*g gradient points, x-major */
+  int32_t n_gauss;          /* g*g: 9, 25 (lite/3x) or 16, 36 (ravu/zoom) */
+  float strength_thr[3];    /* lite/zoom: 0.004 0.016 0.05; 3x: 0.005 0.02 */
+  int32_t n_strength_thr;   /* 0 => log2 form: clamp(floor(log2(lambda*scale + eps)), 0, n_strength-1) */
+  float strength_log2_scale;/* ravu: 2000.0 (ravu-r2.hook:97) */
+  int32_t n_strength;       /* 4 (lite/zoom), 9 (ravu), 3 (3x) */
+  float coherence_thr[2];   /* 0.25 0.5 */
+} mpvp_key_params;
+
+/* Key source for 3-channel planes. */
+#define MPVP_KEY_LUMA 0 /* 1 channel                                   (ravu-r2.hook)      */
+#define MPVP_KEY_YUV 1  /* 3 channels, key from channel 0              (ravu-r2-yuv.hook)  */
+#define MPVP_KEY_RGB 2  /* 3 channels, key from BT.709 luma of rgb     (ravu-r2-rgb.hook:21) */
+
+const char* mpvp_last_error(void);
+int mpvp_abi_version(void);
+/* number of kernels launched by this library since load (all threads); for bench bookkeeping */
+uint64_t mpvp_launch_count(void);
+
+/* ---- weights -------------------------------------------------------------------------- */
+
+/* Upload a //!TEXTURE payload: host_rgba32f is [h][w][4] float32 exactly as decoded from the hex line.
+ * round_to_fp16 != 0 reproduces rgba16f storage (round-to-nearest-even to binary16). */
+int mpvp_weights_create_lut(int device, const float* host_rgba32f, int w, int h, int round_to_fp16,
+                            mpvp_weights** out);
+
+/* Upload one NNEDI3 direction.  w1, w2: [nns][8][win_short] float32 in canonical window order
+ * (index a = offset -3..4 along the long axis, b = offset -(S/2-1)..S/2 along the short axis);
+ * b1, b2: [nns].  The library repacks them into the tcgen05 B-operand layout. */
+int mpvp_weights_create_nnedi3(int device, const float* w1, const float* w2, const float* b1,
+                               const float* b2, int nns, int win_short, mpvp_weights** out);
+
+int mpvp_weights_destroy(mpvp_weights* w);
+
+/* ---- RAVU-Lite (2x luma) ---------------------------------------------------------------- */
+/* in [n][h][w] -> out [n][2h][2w]; phase c of the shader's vec4 goes to (2x + c/2, 2y + c%2). */
+int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                          float ar_strength, const float* in, float* out, int n, int h, int w,
+                          int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                          int64_t out_stride_y, int32_t* bucket_out, void* stream);
+
+/* ---- RAVU (2x, three convolutions + merge, offset -0.5,-0.5) --------------------------------- */
+/* in [n][c][h][w] -> out [n][c][2h][2w], c = 1 (MPVP_KEY_LUMA) or 3.  bucket_out: [n][3][h][w]. */
+int mpvp_ravu_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                     const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
+                     int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                     int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out, void* stream);
+
+/* ---- RAVU-3x ---------------------------------------------------------------------------- */
+/* in [n][c][h][w] -> out [n][c][3h][3w]. bucket_out: [n][h][w]. */
+int mpvp_ravu3x_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                       const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
+                       int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                       int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out, void* stream);
+
+/* ---- RAVU-Zoom (arbitrary ratio) ------------------------------------------------------------ */
+/* in [n][c][h][w] -> out [n][c][out_h][out_w]; lut_ar nullable (non-AR). bucket_out: [n][out_h][out_w]. */
+int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights* lut_ar,
+                          const mpvp_key_params* key, int radius, int key_mode, float ar_strength,
+                          const float* in, float* out, int n, int h, int w, int out_h, int out_w,
+                          int64_t in_stride_n, int64_t in_stride_c, int64_t in_stride_y,
+                          int64_t out_stride_n, int64_t out_stride_c, int64_t out_stride_y,
+                          int32_t* bucket_out, void* stream);
+
+/* ---- NNEDI3 --------------------------------------------------------------------------------- */
+/* One doubling pass.  direction 0 = double_y + combine_y: in [n][h][w] -> out [n][2h][w];
+ * direction 1 = double_x + combine_x: in [n][h][w] -> out [n][h][2w].  `nn` must have been created
+ * from the weights of that direction. */
+int mpvp_nnedi3_launch(const mpvp_weights* nn, int direction, const float* in, float* out, int n,
+                       int h, int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                       int64_t out_stride_y, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end path: H2D + kernel + D2H inside the call) --------- */
+int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                        float ar_strength, const float* host_in, float* host_out, int n, int h,
+                        int w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPVP_H */

@@ -1,0 +1,131 @@
+"""Build and load ``libmpvp.so`` (the C-ABI declared in ``include/mpvp.h``) through ctypes.
+
+There is deliberately no CPU fallback: if the shared library is missing or cannot be loaded every
+entry point raises :class:`NativeError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from typing import List, Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libmpvp.so")
+SOURCES = ["abi.cu", "ravu_lite.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def sources() -> List[str]:
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mpvp.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``libmpvp.so`` (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise NativeError("nvcc not found; cannot build libmpvp.so")
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources() + ["-lcuda"]
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise NativeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+class KeyParams(ctypes.Structure):
+    _fields_ = [
+        ("gauss", ctypes.c_float * 36),
+        ("n_gauss", ctypes.c_int32),
+        ("strength_thr", ctypes.c_float * 3),
+        ("n_strength_thr", ctypes.c_int32),
+        ("strength_log2_scale", ctypes.c_float),
+        ("n_strength", ctypes.c_int32),
+        ("coherence_thr", ctypes.c_float * 2),
+    ]
+
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+_kp = ctypes.POINTER(KeyParams)
+
+# name -> (restype, argtypes): must list every symbol include/mpvp.h declares
+SIGNATURES = {
+    "mpvp_last_error": (ctypes.c_char_p, []),
+    "mpvp_abi_version": (_i, []),
+    "mpvp_launch_count": (ctypes.c_uint64, []),
+    "mpvp_weights_create_lut": (_i, [_i, _vp, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "mpvp_weights_create_nnedi3": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(_vp)]),
+    "mpvp_weights_destroy": (_i, [_vp]),
+    "mpvp_ravu_lite_launch": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "mpvp_ravu_launch": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "mpvp_ravu3x_launch": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "mpvp_ravu_zoom_launch": (_i, [_vp, _vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "mpvp_nnedi3_launch": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
+    "mpvp_ravu_lite_host": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises NativeError (never falls back) if it is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)"
+            )
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise NativeError(f"cannot load {LIB_PATH}: {e}") from None
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                raise NativeError(f"{LIB_PATH} does not export {name}") from None
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mpvp_abi_version() != 1:
+            raise NativeError("libmpvp.so ABI version mismatch; rebuild")
+        _lib = handle
+        return handle
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mpvp_last_error()
+        raise NativeError(f"{what} failed (code {rc}): {msg.decode(errors='replace') if msg else '?'}")

@@ -1,0 +1,397 @@
+"""``prescale()`` -- the Python face of the drop-in boundary.
+
+The reference is used as ``mpv --glsl-shader=ravu-lite-ar-r3.hook`` (``README.md:33-37``): the host
+parses the file, uploads its ``//!TEXTURE`` LUTs once and runs the passes whose ``//!WHEN`` holds on
+every frame.  ``prescale(frames, hook=...)`` does the same for a batch of frames held in a
+``torch.Tensor``: parse (cached) -> plan (WHEN / WIDTH / HEIGHT / OFFSET evaluation) -> upload weights
+(cached per device) -> one fused CUDA kernel per family through the C ABI of ``include/mpvp.h``.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in ``libmpvp.so``.
+There is no CPU fallback: without a CUDA device or without the library this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native
+from .hookfile import HookError, HookFile, Variant, find_hook
+
+__all__ = ["prescale", "plan", "Plan", "upload_weights", "clear_weight_cache"]
+
+
+# ----------------------------------------------------------------------------------------------
+# planning (host logic, no GPU needed)
+# ----------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Plan:
+    """What one application of a hook file does to a (h, w) plane."""
+
+    family: str
+    in_size: Tuple[int, int]  # (h, w)
+    out_size: Tuple[int, int]  # (h, w) actually produced
+    applied: bool
+    offset: Tuple[float, float]  # accumulated //!OFFSET (x, y) in output pixels
+    double_y: bool = False  # nnedi3 only
+    double_x: bool = False
+    passes: Tuple[str, ...] = ()  # DESC strings of the passes that fire
+
+
+def plan(hook: HookFile, in_hw: Tuple[int, int], output_size: Optional[Tuple[int, int]] = None, is_yuv: bool = True) -> Plan:
+    """Evaluate WHEN / WIDTH / HEIGHT / OFFSET of every pass for an (h, w) input.
+
+    ``output_size`` is mpv's OUTPUT (the final target, (h, w)); ``None`` means the hook's natural
+    factor, for which every WHEN of the shipped files holds.  mpv semantics: a pass whose WHEN is false
+    is skipped silently; if none fires the input is returned unchanged (``applied=False``).
+    """
+    v = hook.variant
+    h, w = int(in_hw[0]), int(in_hw[1])
+    if output_size is None:
+        if v.scale is None:
+            raise HookError(f"{hook.name}: ravu-zoom needs output_size=(h, w)")
+        oh, ow = h * v.scale, w * v.scale
+    else:
+        oh, ow = int(output_size[0]), int(output_size[1])
+    env = {"HOOKED": (w, h), "OUTPUT": (ow, oh), "LUMA": (w if is_yuv else 0, h if is_yuv else 0), "NATIVE": (w, h), "MAIN": (w, h)}
+    saved: Dict[str, Tuple[int, int]] = {}
+    fired: List[str] = []
+    off = [0.0, 0.0]
+    dy = dx = False
+    for p in hook.passes:
+        e = dict(env)
+        e.update(saved)
+        if not p.enabled(e):
+            continue
+        size = p.output_size(e)
+        fired.append(p.desc)
+        if p.save:
+            saved[p.save] = size
+        else:
+            env["HOOKED"] = size
+        if isinstance(p.offset, tuple):
+            off[0] += p.offset[0]
+            off[1] += p.offset[1]
+        if "double_y" in p.desc:
+            dy = True
+        if "double_x" in p.desc:
+            dx = True
+    cw, ch = env["HOOKED"]
+    applied = bool(fired)
+    # a chain whose convolution passes were skipped (e.g. the LUMA.w guard of -yuv hooks on non-YUV
+    # input, ravu-r2-yuv.hook:20 vs :326) has nothing to merge: mpv would fail the pass, we skip the hook
+    need = {"ravu": 4, "ravu-lite": 2}.get(v.family)
+    if need is not None and v.flavour == "root" and len(fired) != need:
+        applied = False
+    if not applied:
+        return Plan(v.family, (h, w), (h, w), False, (0.0, 0.0), False, False, ())
+    return Plan(v.family, (h, w), (ch, cw), True, (off[0], off[1]), dy, dx, tuple(fired))
+
+
+# ----------------------------------------------------------------------------------------------
+# weights
+# ----------------------------------------------------------------------------------------------
+
+
+class _Weights:
+    """Device-resident weights of one hook on one device (opaque C handles)."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.handles: Dict[str, ctypes.c_void_p] = {}
+        self.key = _native.KeyParams()
+
+    def close(self):
+        lib = _native.lib()
+        for h in self.handles.values():
+            lib.mpvp_weights_destroy(h)
+        self.handles.clear()
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_wcache: Dict[Tuple[str, int, str], _Weights] = {}
+_wlock = threading.Lock()
+
+
+def _key_params(v: Variant) -> _native.KeyParams:
+    kp = _native.KeyParams()
+    g = np.asarray(v.gauss, dtype=np.float32)
+    for i, val in enumerate(g):
+        kp.gauss[i] = float(val)
+    kp.n_gauss = len(g)
+    for i, t in enumerate(v.strength_thr):
+        kp.strength_thr[i] = float(t)
+    kp.n_strength_thr = len(v.strength_thr)
+    kp.strength_log2_scale = float(v.strength_log2_scale)
+    kp.n_strength = int(v.n_strength)
+    kp.coherence_thr[0], kp.coherence_thr[1] = (float(t) for t in v.coherence_thr)
+    return kp
+
+
+def upload_weights(hook: HookFile, device: int, lut_precision: str = "fp16") -> _Weights:
+    if lut_precision not in ("fp16", "fp32"):
+        raise ValueError("lut_precision must be 'fp16' or 'fp32'")
+    key = (hook.path, device, lut_precision)
+    with _wlock:
+        hit = _wcache.get(key)
+        if hit is not None:
+            return hit
+        lib = _native.lib()
+        v = hook.variant
+        W = _Weights(device)
+        if v.family == "nnedi3":
+            for name, nn in (("y", v.nn_y), ("x", v.nn_x)):
+                arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (nn.w1, nn.w2, nn.b1, nn.b2)]
+                h = ctypes.c_void_p()
+                rc = lib.mpvp_weights_create_nnedi3(device, *(a.ctypes.data for a in arrs), v.nns, v.win[1], ctypes.byref(h))
+                _native.check(rc, "mpvp_weights_create_nnedi3")
+                W.handles[name] = h
+        else:
+            W.key = _key_params(v)
+            for name, tex in (("lut", v.lut), ("lut_ar", v.lut_ar)):
+                if tex is None:
+                    continue
+                data = np.ascontiguousarray(tex.data, dtype=np.float32)
+                h = ctypes.c_void_p()
+                rc = lib.mpvp_weights_create_lut(device, data.ctypes.data, tex.width, tex.height, 1 if lut_precision == "fp16" else 0, ctypes.byref(h))
+                _native.check(rc, "mpvp_weights_create_lut")
+                W.handles[name] = h
+        _wcache[key] = W
+        return W
+
+
+def clear_weight_cache() -> None:
+    with _wlock:
+        for W in _wcache.values():
+            W.close()
+        _wcache.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# launch
+# ----------------------------------------------------------------------------------------------
+
+
+def _launch(hook: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, want_buckets: bool):
+    """x: float32 CUDA tensor [N, C, H, W] contiguous in (H, W).  Returns (out, buckets|None)."""
+    lib = _native.lib()
+    v = hook.variant
+    dev = x.device.index
+    n, c, h, w = x.shape
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    oh, ow = pl.out_size
+    key_mode = {"luma": 0, "yuv": 1, "rgb": 2}[v.plane]
+    bk = None
+    bptr = None
+
+    def out_tensor(hh, ww):
+        return torch.empty((n, c, hh, ww), dtype=torch.float32, device=x.device)
+
+    if v.family == "ravu-lite":
+        out = out_tensor(oh, ow)
+        if want_buckets:
+            bk = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
+            bptr = bk.data_ptr()
+        rc = lib.mpvp_ravu_lite_launch(
+            W.handles["lut"], ctypes.byref(W.key), v.radius, 1 if v.ar else 0, float(v.ar_strength),
+            x.data_ptr(), out.data_ptr(), n, h, w, x.stride(0), x.stride(2), out.stride(0), out.stride(2), bptr, stream)
+        _native.check(rc, "mpvp_ravu_lite_launch")
+        return out, bk
+    if v.family in ("ravu", "ravu-3x"):
+        out = out_tensor(oh, ow)
+        if want_buckets:
+            bk = torch.empty((n, 3, h, w) if v.family == "ravu" else (n, h, w), dtype=torch.int32, device=x.device)
+            bptr = bk.data_ptr()
+        fn = lib.mpvp_ravu_launch if v.family == "ravu" else lib.mpvp_ravu3x_launch
+        rc = fn(W.handles["lut"], ctypes.byref(W.key), v.radius, key_mode, x.data_ptr(), out.data_ptr(), n, h, w,
+                x.stride(0), x.stride(1), x.stride(2), out.stride(0), out.stride(1), out.stride(2), bptr, stream)
+        _native.check(rc, "mpvp_ravu_launch" if v.family == "ravu" else "mpvp_ravu3x_launch")
+        return out, bk
+    if v.family == "ravu-zoom":
+        out = out_tensor(oh, ow)
+        if want_buckets:
+            bk = torch.empty((n, oh, ow), dtype=torch.int32, device=x.device)
+            bptr = bk.data_ptr()
+        rc = lib.mpvp_ravu_zoom_launch(
+            W.handles["lut"], W.handles.get("lut_ar"), ctypes.byref(W.key), v.radius, key_mode, float(v.ar_strength),
+            x.data_ptr(), out.data_ptr(), n, h, w, oh, ow, x.stride(0), x.stride(1), x.stride(2),
+            out.stride(0), out.stride(1), out.stride(2), bptr, stream)
+        _native.check(rc, "mpvp_ravu_zoom_launch")
+        return out, bk
+    if v.family == "nnedi3":
+        cur = x.reshape(n * c, h, w)
+        if pl.double_y:
+            nxt = torch.empty((n * c, 2 * cur.shape[1], cur.shape[2]), dtype=torch.float32, device=x.device)
+            rc = lib.mpvp_nnedi3_launch(W.handles["y"], 0, cur.data_ptr(), nxt.data_ptr(), cur.shape[0], cur.shape[1], cur.shape[2],
+                                        cur.stride(0), cur.stride(1), nxt.stride(0), nxt.stride(1), stream)
+            _native.check(rc, "mpvp_nnedi3_launch(y)")
+            cur = nxt
+        if pl.double_x:
+            nxt = torch.empty((n * c, cur.shape[1], 2 * cur.shape[2]), dtype=torch.float32, device=x.device)
+            rc = lib.mpvp_nnedi3_launch(W.handles["x"], 1, cur.data_ptr(), nxt.data_ptr(), cur.shape[0], cur.shape[1], cur.shape[2],
+                                        cur.stride(0), cur.stride(1), nxt.stride(0), nxt.stride(1), stream)
+            _native.check(rc, "mpvp_nnedi3_launch(x)")
+            cur = nxt
+        return cur.reshape(n, c, cur.shape[1], cur.shape[2]), None
+    raise HookError(f"unsupported family {v.family}")
+
+
+def _normalise_input(frames: torch.Tensor, v: Variant) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    if not isinstance(frames, torch.Tensor):
+        raise TypeError("frames must be a torch.Tensor")
+    if frames.dtype != torch.float32:
+        raise TypeError(f"frames must be float32 in [0, 1] (got {frames.dtype})")
+    shape = tuple(frames.shape)
+    c = v.channels
+    if c == 1:
+        if frames.dim() == 2:
+            x = frames[None, None]
+        elif frames.dim() == 3:
+            x = frames[:, None]
+        elif frames.dim() == 4 and frames.shape[1] == 1:
+            x = frames
+        else:
+            raise ValueError(f"luma hook expects [H,W], [N,H,W] or [N,1,H,W]; got {shape}")
+    else:
+        if frames.dim() == 3 and frames.shape[0] == 3:
+            x = frames[None]
+        elif frames.dim() == 4 and frames.shape[1] == 3:
+            x = frames
+        else:
+            raise ValueError(f"{v.plane} hook expects planar [3,H,W] or [N,3,H,W]; got {shape}")
+    if x.shape[2] < 1 or x.shape[3] < 1:
+        raise ValueError(f"empty plane {shape}")
+    return x, shape
+
+
+def _restore_shape(out: torch.Tensor, in_shape: Tuple[int, ...], c: int) -> torch.Tensor:
+    if c == 1:
+        if len(in_shape) == 2:
+            return out[0, 0]
+        if len(in_shape) == 3:
+            return out[:, 0]
+        return out
+    return out[0] if len(in_shape) == 3 else out
+
+
+def prescale(
+    frames: torch.Tensor,
+    hook: Union[str, "HookFile"] = "ravu-lite-ar-r3.hook",
+    output_size: Optional[Tuple[int, int]] = None,
+    devices: Optional[Sequence[Union[int, str, torch.device]]] = None,
+    lut_precision: str = "fp16",
+    return_buckets: bool = False,
+    is_yuv: bool = True,
+    out: Optional[torch.Tensor] = None,
+):
+    """Apply one mpv-prescalers hook file to a batch of frames.
+
+    frames        float32 in [0,1]; luma hooks: ``[H,W]``, ``[N,H,W]`` or ``[N,1,H,W]``; ``-yuv``/``-rgb``
+                  hooks: planar ``[3,H,W]`` or ``[N,3,H,W]``.  CUDA tensors are processed in place on their
+                  device and the result stays there; CPU tensors are staged through the GPU (host->device
+                  copy, kernel, device->host copy) and a CPU tensor is returned.
+    hook          path or bare name of a shipped ``.hook`` file (root, ``gather/`` or ``compute/`` flavour).
+    output_size   mpv's OUTPUT size ``(h, w)`` used by the ``//!WHEN`` conditions; required for ravu-zoom
+                  (it is the size produced); ``None`` = the hook's natural 2x / 3x.
+    devices       shard the batch dimension over these GPUs (frames are independent, no collective);
+                  returns a list with one output tensor per device (outputs stay on their GPU).
+    lut_precision 'fp16' reproduces the reference's rgba16f LUT storage; 'fp32' keeps the file's floats.
+    out           optional destination for CPU inputs: a (pinned) float32 CPU tensor ``[N,C,OH,OW]`` that
+                  receives the result, so that a video loop does not re-allocate pinned memory per batch.
+
+    Returns the output tensor (same rank as the input) carrying ``.offset`` (accumulated ``//!OFFSET``,
+    (x, y) in output pixels), ``.applied`` and ``.plan``; with ``return_buckets=True`` a pair
+    ``(out, buckets)`` where ``buckets`` holds the LUT row of every key evaluation (RAVU families).
+    """
+    hk = hook if isinstance(hook, HookFile) else HookFile.parse(find_hook(hook))
+    v = hk.variant
+    if devices is not None:
+        from .sharding import prescale_sharded
+
+        return prescale_sharded(frames, hk, output_size, list(devices), lut_precision, is_yuv)
+    x, in_shape = _normalise_input(frames, v)
+    n, c, h, w = x.shape
+    pl = plan(hk, (h, w), output_size, is_yuv)
+    if not pl.applied:
+        out = frames
+        out.offset, out.applied, out.plan = (0.0, 0.0), False, pl
+        return (out, None) if return_buckets else out
+    if not torch.cuda.is_available():
+        raise _native.NativeError("prescale() needs a CUDA device: there is no CPU fallback")
+    host_input = x.device.type != "cuda"
+    if host_input:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        W = upload_weights(hk, dev.index, lut_precision)
+        res, bk = _prescale_host(hk, pl, x, W, dev, return_buckets, out)
+    else:
+        dev = x.device
+        xd = x if (x.stride(3) == 1 and x.stride(2) >= w) else x.contiguous()
+        W = upload_weights(hk, dev.index, lut_precision)
+        with torch.cuda.device(dev):
+            res, bk = _launch(hk, pl, xd, W, return_buckets)
+    res = _restore_shape(res, in_shape, c)
+    res.offset, res.applied, res.plan = pl.offset, True, pl
+    return (res, bk) if return_buckets else res
+
+
+_host_streams: Dict[int, List[torch.cuda.Stream]] = {}
+
+
+def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: torch.device, want_buckets: bool,
+                   out: Optional[torch.Tensor]):
+    """CPU tensor in, CPU tensor out: frames are staged through the GPU in chunks on two streams so that the
+    host->device copy of chunk k+1 and the device->host copy of chunk k-1 overlap the kernel of chunk k
+    (effective only with pinned host memory)."""
+    n, c, h, w = x.shape
+    oh, ow = pl.out_size
+    if hk.variant.family == "nnedi3":
+        oh, ow = h * (2 if pl.double_y else 1), w * (2 if pl.double_x else 1)
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((n, c, oh, ow), dtype=torch.float32, pin_memory=True)
+    elif tuple(out.shape) != (n, c, oh, ow) or out.dtype != torch.float32 or out.device.type != "cpu":
+        raise ValueError(f"out must be a float32 CPU tensor of shape {(n, c, oh, ow)}")
+    bks = torch.empty((n,) + _bucket_shape(hk.variant, h, w, oh, ow), dtype=torch.int32) if want_buckets else None
+    if bks is not None and hk.variant.family == "nnedi3":
+        bks = None
+    streams = _host_streams.get(dev.index)
+    if streams is None:
+        streams = _host_streams[dev.index] = [torch.cuda.Stream(dev) for _ in range(2)]
+    frame_bytes = 4 * c * (h * w + oh * ow)
+    chunk = max(1, min(n, (256 << 20) // max(frame_bytes, 1)))
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        for s in streams:
+            s.wait_stream(cur)
+        for k, f0 in enumerate(range(0, n, chunk)):
+            f1 = min(n, f0 + chunk)
+            s = streams[k & 1]
+            with torch.cuda.stream(s):
+                xd = x[f0:f1].to(dev, non_blocking=True)
+                od, bd = _launch(hk, pl, xd, W, want_buckets and bks is not None)
+                out[f0:f1].copy_(od, non_blocking=True)
+                if bd is not None:
+                    bks[f0:f1].copy_(bd, non_blocking=True)
+                del xd, od, bd
+        for s in streams:
+            s.synchronize()
+    return out, bks
+
+
+def _bucket_shape(v: Variant, h: int, w: int, oh: int, ow: int) -> Tuple[int, ...]:
+    if v.family == "ravu":
+        return (3, h, w)
+    if v.family == "ravu-zoom":
+        return (oh, ow)
+    return (h, w)

@@ -1,0 +1,168 @@
+// Shared host/device helpers for libmpvp (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/mpvp.h"
+
+namespace mpvp {
+
+// ---- error reporting ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define MPVP_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::mpvp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MPVP_E_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define MPVP_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::mpvp::set_error(__VA_ARGS__);    \
+      return MPVP_E_INVALID;             \
+    }                                    \
+  } while (0)
+
+// RAII device switch: launches run on the device that owns the weights.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int sm_count(int device);
+
+}  // namespace mpvp
+
+// Opaque handle behind mpvp_weights*.
+struct mpvp_weights {
+  int device = 0;
+  int kind = 0;  // 0 = LUT, 1 = NNEDI3
+  // LUT: rows x texels_per_row float4 (values already rounded to fp16 precision if requested)
+  float* lut = nullptr;
+  int lut_w = 0, lut_h = 0;
+  cudaTextureObject_t tex = 0;  // zoom: float4 2-D array texture, LINEAR, clamp
+  cudaArray_t tex_array = nullptr;
+  // NNEDI3
+  int nns = 0, win_short = 0;
+  void* nn_b = nullptr;     // packed fp16 B operand(s) for tcgen05
+  float* nn_bias = nullptr; // [2*nns] interleaved (b1*log2e, b2)
+  float* nn_w = nullptr;    // fp32 copy [2*nns][K] (reference SIMT path / debugging)
+  size_t nn_b_bytes = 0;
+};
+
+namespace mpvp {
+
+// ---- RAVU key (structure tensor -> LUT row) --------------------------------------------------
+// Every operation below is an explicitly rounded IEEE fp32 op in the operand order of the shader
+// text (ravu-lite-ar-r3.hook:48-88, ravu-r3.hook:58-119): no FMA contraction, correctly rounded
+// sqrt / division.  The >= 99.99 % bucket-agreement rule leaves no room for re-association
+// (SURVEY.md section 7.4 item 2, App. H16).
+
+constexpr float kEps = 1.192092896e-7f;
+constexpr float kPi = 3.141592653589793f;
+
+enum Stencil { STENCIL_LITE = 0, STENCIL_RAVU = 1 };
+
+// One finite difference along an axis; S(d) returns the sample at offset d along that axis.
+template <int FAMILY, int N, class SF>
+__device__ __forceinline__ float key_diff(int k, SF S) {
+  if (FAMILY == STENCIL_RAVU && k - 2 >= 0 && k + 2 <= N - 1) {
+    // (-s[+2] + 8.0*s[+1] - 8.0*s[-1] + s[-2]) / 12.0
+    float t = __fadd_rn(-S(2), __fmul_rn(8.0f, S(1)));
+    t = __fsub_rn(t, __fmul_rn(8.0f, S(-1)));
+    t = __fadd_rn(t, S(-2));
+    return __fdiv_rn(t, 12.0f);
+  }
+  if (k - 1 >= 0 && k + 1 <= N - 1) return __fmul_rn(__fsub_rn(S(1), S(-1)), 0.5f);
+  if (k - 1 < 0) return __fsub_rn(S(1), S(0));
+  return __fsub_rn(S(0), S(-1));
+}
+
+struct KeyOut {
+  int row;
+};
+
+// a, b, d -> LUT row.  NTHR = number of strength thresholds (0 => log2 form).
+__device__ __forceinline__ int key_from_abd(const mpvp_key_params& kp, float a, float b, float d) {
+  const float T = __fadd_rn(a, d);
+  const float D = __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, b));
+  const float delta = __fsqrt_rn(fmaxf(__fsub_rn(__fmul_rn(__fmul_rn(T, T), 0.25f), D), 0.0f));
+  const float halfT = __fmul_rn(T, 0.5f);
+  const float L1 = __fadd_rn(halfT, delta);
+  const float L2 = __fsub_rn(halfT, delta);
+  const float sqrtL1 = __fsqrt_rn(L1);
+  const float sqrtL2 = __fsqrt_rn(L2);  // NaN for a tiny negative L2, deliberately kept (App. D.2)
+  float theta;
+  if (fabsf(b) < kEps) {
+    theta = 0.0f;
+  } else {
+    const float at = __fadd_rn(atan2f(__fsub_rn(L1, a), b), kPi);
+    theta = __fsub_rn(at, __fmul_rn(kPi, floorf(__fdiv_rn(at, kPi))));
+  }
+  const float ssum = __fadd_rn(sqrtL1, sqrtL2);
+  float mu = __fdiv_rn(__fsub_rn(sqrtL1, sqrtL2), ssum);
+  if (ssum < kEps) mu = 0.0f;
+  const float angle = floorf(__fdiv_rn(__fmul_rn(theta, 24.0f), kPi));
+  float strength;
+  if (kp.n_strength_thr > 0) {
+    strength = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < kp.n_strength_thr && sqrtL1 >= kp.strength_thr[i]) strength += 1.0f;
+  } else {
+    strength = floorf(log2f(__fadd_rn(__fmul_rn(sqrtL1, kp.strength_log2_scale), kEps)));
+    strength = fminf(fmaxf(strength, 0.0f), (float)(kp.n_strength - 1));
+  }
+  const float coh = (mu >= kp.coherence_thr[0] ? 1.0f : 0.0f) + (mu >= kp.coherence_thr[1] ? 1.0f : 0.0f);
+  float rowf = (angle * (float)kp.n_strength + strength) * 3.0f + coh;
+  const int nrows = 24 * kp.n_strength * 3;
+  if (!(rowf >= 0.0f)) rowf = 0.0f;  // also catches NaN
+  int row = (int)rowf;
+  return row > nrows - 1 ? nrows - 1 : row;
+}
+
+// Full key for an N x N window whose sample (i, j) [i <-> dx, j <-> dy] is W(i, j).
+template <int FAMILY, int N, int G, class WF>
+__device__ __forceinline__ int ravu_key(const mpvp_key_params& kp, WF W) {
+  constexpr int O = (N - G) / 2;
+  float a = 0.0f, b = 0.0f, d = 0.0f;
+#pragma unroll
+  for (int i = O; i < O + G; ++i) {
+#pragma unroll
+    for (int j = O; j < O + G; ++j) {
+      const float gx = key_diff<FAMILY, N>(i, [&](int dd) { return W(i + dd, j); });
+      const float gy = key_diff<FAMILY, N>(j, [&](int dd) { return W(i, j + dd); });
+      const float g = kp.gauss[(i - O) * G + (j - O)];
+      a = __fadd_rn(a, __fmul_rn(__fmul_rn(gx, gx), g));
+      b = __fadd_rn(b, __fmul_rn(__fmul_rn(gx, gy), g));
+      d = __fadd_rn(d, __fmul_rn(__fmul_rn(gy, gy), g));
+    }
+  }
+  return key_from_abd(kp, a, b, d);
+}
+
+__device__ __forceinline__ float pow32(float c) {
+  c *= c; c *= c; c *= c; c *= c; c *= c;
+  return c;
+}
+
+__host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+}  // namespace mpvp

@@ -1,0 +1,250 @@
+// RAVU (non-lite): the four reference passes in ONE kernel.
+//
+//   step1  int11 = value at (x+1/2, y+1/2)         ravu-r2.hook:15-114   (rgb: ravu-r2-rgb.hook:15-131)
+//   step2  int10 = value at (x+1/2, y)             ravu-r2.hook:115-215  (45-degree rotated lattice)
+//   step3  int01 = value at (x, y+1/2)             ravu-r2.hook:216-316
+//   step4  merge into 2W x 2H, OFFSET -0.5 -0.5    ravu-r2.hook:317-338
+//
+// A CTA owns a 64x32 tile of input pixels.  Phase A computes int11 on the tile plus the halo that
+// steps 2/3 will tap ((64+2r-1) x (32+2r-1) positions) into shared memory; positions outside the
+// image replicate the border int11 value (clamp-to-edge on the *saved texture*),
+// which is done by evaluating int11 at the clamped coordinate.  Phase B computes int10 and int01
+// from the staged HOOKED tile and the int11 tile and writes the interleaved 2x2 block.  int11 never
+// touches HBM.  -yuv / -rgb variants carry three colour planes plus the key plane.
+#include "common.cuh"
+
+namespace mpvp {
+namespace {
+
+struct RavuArgs {
+  const float* __restrict__ in;
+  float* __restrict__ out;
+  const float4* __restrict__ lut;  // [648][LW]
+  int32_t* __restrict__ bucket;    // [n][3][h][w] or null
+  int n, h, w;
+  int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+  mpvp_key_params key;
+};
+
+constexpr int kTW = 64, kTH = 32;
+constexpr float kCp0 = 0.2126f, kCp1 = 0.7152f, kCp2 = 0.0722f;
+
+__device__ __forceinline__ float rgb_luma(float r, float g, float b) {
+  // dot(rgb, color_primary) evaluated left to right without contraction (ravu-r2-rgb.hook:24)
+  return __fadd_rn(__fadd_rn(__fmul_rn(r, kCp0), __fmul_rn(g, kCp1)), __fmul_rn(b, kCp2));
+}
+
+// One key + convolution.  KS(t) = key sample t, CS(c, t) = colour sample of channel c.
+template <int R, int C, class KF, class CF>
+__device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4* __restrict__ s_lut, KF KS, CF CS,
+                                         float (&res)[C]) {
+  constexpr int N = 2 * R, TAPS = N * N, G = (R == 4) ? 6 : 4;
+  constexpr int LW = (TAPS / 2 + 3) / 4;
+  float ks[TAPS];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) ks[t] = KS(t);
+  const int row = ravu_key<STENCIL_RAVU, N, G>(kp, [&](int i, int j) { return ks[i * N + j]; });
+  const float4* __restrict__ wrow = s_lut + row * LW;
+#pragma unroll
+  for (int c = 0; c < C; ++c) res[c] = 0.f;
+#pragma unroll
+  for (int q = 0; q < LW; ++q) {
+    const float4 w4 = wrow[q];
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = q * 4 + e;
+      if (k < TAPS / 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float sa = (C == 1) ? ks[k] : CS(c, k);
+          const float sb = (C == 1) ? ks[TAPS - 1 - k] : CS(c, TAPS - 1 - k);
+          res[c] = fmaf(sa + sb, wv[e], res[c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) res[c] = fminf(fmaxf(res[c], 0.f), 1.f);
+  return row;
+}
+
+// KEYMODE: 0 luma (C=1), 1 yuv (key = channel 0), 2 rgb (key = BT.709 luma)
+template <int R, int C, int KEYMODE, int NT>
+__global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
+  constexpr int N = 2 * R, TAPS = N * N;
+  constexpr int LW = (TAPS / 2 + 3) / 4;
+  constexpr int HH = 2 * R - 1;              // HOOKED halo
+  constexpr int HW_ = kTW + 2 * HH, HHt = kTH + 2 * HH;   // staged HOOKED tile
+  constexpr int IW = kTW + 2 * R - 1, IH = kTH + 2 * R - 1;  // int11 tile: x' in [x0-R, x0+TW+R-2]
+  constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);  // planes: colours (+ key plane for rgb)
+  constexpr int KP = (C == 1) ? 0 : ((KEYMODE == 2) ? 3 : 0);  // index of the key plane
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_lut = reinterpret_cast<float4*>(smem_raw);
+  float* s_h = reinterpret_cast<float*>(smem_raw + sizeof(float4) * 648 * LW);  // [NP][HHt][HW_]
+  float* s_i = s_h + NP * HHt * HW_;                                             // [NP][IH][IW]
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 648 * LW; i += NT) s_lut[i] = A.lut[i];
+
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+    const int tix = (int)(tile % A.tiles_x);
+    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
+    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const int x0 = tix * kTW, y0 = tiy * kTH;
+    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+
+    __syncthreads();
+    // ---- stage HOOKED (clamp-to-edge) ---------------------------------------------------
+    for (int i = tid; i < HW_ * HHt; i += NT) {
+      const int sy = i / HW_, sx = i - sy * HW_;
+      const int gx = clampi(x0 + sx - HH, 0, A.w - 1);
+      const int gy = clampi(y0 + sy - HH, 0, A.h - 1);
+      const int64_t off = (int64_t)gy * A.in_sy + gx;
+      if (C == 1) {
+        s_h[i] = __ldg(src + off);
+      } else {
+        const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
+        s_h[i] = c0;
+        s_h[HHt * HW_ + i] = c1;
+        s_h[2 * HHt * HW_ + i] = c2;
+        if (KEYMODE == 2) s_h[3 * HHt * HW_ + i] = rgb_luma(c0, c1, c2);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase A: int11 on the tile + halo ------------------------------------------------
+    for (int i = tid; i < IW * IH; i += NT) {
+      const int iy = i / IW, ix = i - iy * IW;
+      const int px = x0 - R + ix, py = y0 - R + iy;          // int11 texel this slot stands for
+      const int cx = clampi(px, 0, A.w - 1), cy = clampi(py, 0, A.h - 1);
+      // staged coordinates of the window origin (tap offset -(R-1))
+      const int bx = cx - (R - 1) - (x0 - HH), by = cy - (R - 1) - (y0 - HH);
+      const float* __restrict__ kb = s_h + KP * HHt * HW_ + by * HW_ + bx;
+      const float* __restrict__ cb = s_h + by * HW_ + bx;
+      float res[C];
+      const int row = ravu_conv<R, C>(
+          A.key, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
+          [&](int c, int t) { return cb[c * HHt * HW_ + (t % N) * HW_ + (t / N)]; }, res);
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_i[c * IH * IW + i] = res[c];
+      if (KEYMODE == 2) s_i[3 * IH * IW + i] = rgb_luma(res[0], res[C > 1 ? 1 : 0], res[C > 2 ? 2 : 0]);
+      if (A.bucket && px == cx && py == cy && px >= x0 && px < x0 + kTW && py >= y0 && py < y0 + kTH)
+        A.bucket[(((int64_t)f * 3 + 0) * A.h + py) * A.w + px] = row;
+    }
+    __syncthreads();
+
+    // ---- phase B: int10 / int01 + merge ---------------------------------------------------
+    for (int i = tid; i < kTW * kTH; i += NT) {
+      const int ly = i / kTW, lx = i - ly * kTW;
+      const int x = x0 + lx, y = y0 + ly;
+      if (x >= A.w || y >= A.h) continue;
+      const float* __restrict__ hb = s_h + (ly + HH) * HW_ + (lx + HH);  // HOOKED(x, y)
+      const float* __restrict__ ib = s_i + (ly + R) * IW + (lx + R);     // int11(x, y)
+      float r10[C], r01[C];
+      int rows[2];
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int tx2 = pass == 0 ? 1 : 0, ty2 = pass == 0 ? 0 : 1;
+        // sample t=(i,j): twice the real position = (tx2 - (2R-1) + i + j, ty2 - i + j)
+        auto fetch = [&](int plane, int t) -> float {
+          const int ii = t / N, jj = t % N;
+          const int px2 = tx2 - (2 * R - 1) + ii + jj, py2 = ty2 - ii + jj;
+          if ((px2 & 1) == 0) return hb[plane * HHt * HW_ + (py2 / 2) * HW_ + (px2 / 2)];
+          return ib[plane * IH * IW + ((py2 - 1) / 2) * IW + ((px2 - 1) / 2)];
+        };
+        rows[pass] = ravu_conv<R, C>(
+            A.key, s_lut, [&](int t) { return fetch(KP, t); }, [&](int c, int t) { return fetch(c, t); },
+            pass == 0 ? r10 : r01);
+      }
+      if (A.bucket) {
+        A.bucket[(((int64_t)f * 3 + 1) * A.h + y) * A.w + x] = rows[0];
+        A.bucket[(((int64_t)f * 3 + 2) * A.h + y) * A.w + x] = rows[1];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float* __restrict__ o = A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(2 * y) * A.out_sy + 2 * x;
+        // (2x,2y)=HOOKED (2x+1,2y)=int10 (2x,2y+1)=int01 (2x+1,2y+1)=int11   (ravu-r2.hook:327-338)
+        __stcs(reinterpret_cast<float2*>(o), make_float2(hb[c * HHt * HW_], r10[c]));
+        __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(r01[c], ib[c * IH * IW]));
+      }
+    }
+  }
+}
+
+template <int R, int C, int KEYMODE, int NT>
+int launch_ravu(const RavuArgs& a0, int device, cudaStream_t stream) {
+  constexpr int N = 2 * R, TAPS = N * N, LW = (TAPS / 2 + 3) / 4, HH = 2 * R - 1;
+  constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
+  const size_t smem = sizeof(float4) * 648 * LW +
+                      sizeof(float) * NP * ((kTW + 2 * HH) * (kTH + 2 * HH) + (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
+  RavuArgs a = a0;
+  a.tiles_x = (a.w + kTW - 1) / kTW;
+  a.tiles_y = (a.h + kTH - 1) / kTH;
+  a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  auto kern = ravu_kernel<R, C, KEYMODE, NT>;
+  MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) {
+    set_error("ravu kernel does not fit on an SM (smem %zu B)", smem);
+    return MPVP_E_UNSUPPORTED;
+  }
+  long long grid = (long long)sm_count(device) * per_sm;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid < 1) return MPVP_OK;
+  kern<<<(unsigned)grid, NT, smem, stream>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MPVP_CUDA_OK(cudaGetLastError());
+  return MPVP_OK;
+}
+
+}  // namespace
+}  // namespace mpvp
+
+using namespace mpvp;
+
+extern "C" int mpvp_ravu_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                                const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
+                                int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
+                                int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  MPVP_REQUIRE(lut && lut->kind == 0 && lut->lut, "lut handle is null or not a LUT");
+  MPVP_REQUIRE(key && in && out, "null argument");
+  MPVP_REQUIRE(radius >= 2 && radius <= 4, "radius %d not in {2,3,4}", radius);
+  MPVP_REQUIRE(key_mode >= 0 && key_mode <= 2, "key_mode %d", key_mode);
+  MPVP_REQUIRE(n >= 0 && h >= 1 && w >= 1, "bad frame geometry n=%d h=%d w=%d", n, h, w);
+  const int taps = 4 * radius * radius, g = radius == 4 ? 6 : 4;
+  MPVP_REQUIRE(lut->lut_w == (taps / 2 + 3) / 4 && lut->lut_h == 648, "LUT is %dx%d, expected %dx648", lut->lut_w,
+               lut->lut_h, (taps / 2 + 3) / 4);
+  MPVP_REQUIRE(key->n_gauss == g * g && key->n_strength == 9 && key->n_strength_thr == 0,
+               "key params do not describe a RAVU (log2-strength) hook");
+  MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (out_stride_c % 2) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) % 8) == 0,
+               "output rows must be 8-byte aligned (even strides)");
+  if (n == 0) return MPVP_OK;
+  DeviceGuard guard(lut->device);
+  MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
+  RavuArgs a{};
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.n = n; a.h = h; a.w = w;
+  a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
+  a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;
+  a.key = *key;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dev = lut->device;
+  switch (radius * 3 + key_mode) {
+    case 6: return launch_ravu<2, 1, 0, 512>(a, dev, st);
+    case 7: return launch_ravu<2, 3, 1, 512>(a, dev, st);
+    case 8: return launch_ravu<2, 3, 2, 512>(a, dev, st);
+    case 9: return launch_ravu<3, 1, 0, 512>(a, dev, st);
+    case 10: return launch_ravu<3, 3, 1, 256>(a, dev, st);
+    case 11: return launch_ravu<3, 3, 2, 256>(a, dev, st);
+    case 12: return launch_ravu<4, 1, 0, 256>(a, dev, st);
+    case 13: return launch_ravu<4, 3, 1, 256>(a, dev, st);
+    case 14: return launch_ravu<4, 3, 2, 256>(a, dev, st);
+  }
+  return MPVP_E_INVALID;
+}

@@ -1,0 +1,389 @@
+// RAVU-Lite(-AR) and RAVU-3x: one fused kernel per call.
+//
+// Reference passes replaced (all of them in ONE launch, nothing round-trips HBM):
+//   RAVU-Lite(-AR) step1 + step2        ravu-lite-ar-r3.hook:15-197   (compute form :22-170)
+//   RAVU-3x                             compute/ravu-3x-r2.hook:15-115
+//
+// Design (B200): persistent CTAs (grid = SMs x resident CTAs) walk a (frame, tile) work list.  The
+// whole LUT lives in shared memory for the lifetime of the CTA (r3: 288 x 13 float4 = 58.5 KB;
+// values are exactly the fp16-rounded texels the reference's rgba16f texture holds).  A CTA stages
+// one input tile + halo in shared memory (clamp-to-edge applied while staging), then every thread
+// walks a vertical strip of P pixels keeping the (P + 2o) x n luma window in registers, so that
+// gradients, and the (0.1+l)^32 / (1.1-l)^32 anti-ringing powers are computed once per source
+// pixel and reused by every output pixel that taps them.  All 4 (or 9) sub-pixel phases are
+// written interleaved with 8-byte coalesced streaming stores.
+#include "common.cuh"
+
+namespace mpvp {
+namespace {
+
+struct LiteArgs {
+  const float* __restrict__ in;
+  float* __restrict__ out;
+  const float4* __restrict__ lut;  // [rows][LW]
+  int32_t* __restrict__ bucket;
+  int n, h, w;
+  int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+  float ar_strength;
+  mpvp_key_params key;
+};
+
+template <int R>
+struct LiteGeom {
+  static constexpr int N = 2 * R - 1;                 // window side
+  static constexpr int O = R - 1;                     // halo
+  static constexpr int G = (R == 4) ? 5 : 3;          // gradient square side
+  static constexpr int TAPS = N * N;
+  static constexpr int HALF = (TAPS - 1) / 2;
+};
+
+// Is window tap t (x-major) inside the anti-ringing diamond dx^2 + dy^2 <= 4 ?
+template <int R>
+__device__ __forceinline__ constexpr bool ar_tap(int t) {
+  const int dx = t / (2 * R - 1) - (R - 1), dy = t % (2 * R - 1) - (R - 1);
+  return dx * dx + dy * dy <= 4;
+}
+
+constexpr int kTW = 64;       // tile width  (input pixels)
+constexpr int kThreads = 256; // 64 x 4 threads
+
+__device__ __forceinline__ float rgb_luma709(float r, float g, float b) {
+  // dot(rgb, color_primary), left to right, no contraction (compute/ravu-3x-r2-rgb.hook:23,33)
+  return __fadd_rn(__fadd_rn(__fmul_rn(r, 0.2126f), __fmul_rn(g, 0.7152f)), __fmul_rn(b, 0.0722f));
+}
+
+// C = colour channels (1 or 3; 3 only for SCALE == 3), KEYMODE: 0 luma, 1 yuv (key = channel 0), 2 rgb
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE>
+__global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : 2))
+ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
+  static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
+  using Gm = LiteGeom<R>;
+  constexpr int N = Gm::N, O = Gm::O, G = Gm::G, TAPS = Gm::TAPS, HALF = Gm::HALF;
+  constexpr int LW = (SCALE == 2) ? (TAPS + 1) / 2 : (TAPS + 1);
+  constexpr int ROWS = (SCALE == 2) ? 288 : 216;
+  constexpr int TR = kThreads / kTW;          // thread rows
+  constexpr int TH = TR * P * STRIPS;         // tile height
+  constexpr int SW = kTW + 2 * O;             // staged tile width
+  constexpr int SH = TH + 2 * O;
+  constexpr int PLANE = SW * SH;              // plane 0 = key plane, planes 1..3 = colours (C == 3)
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_lut = reinterpret_cast<float4*>(smem_raw);
+  float* s_tile = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LW);
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[i] = A.lut[i];
+
+  const int tx = tid % kTW, tr = tid / kTW;
+
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+    const int tix = (int)(tile % A.tiles_x);
+    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
+    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const int x0 = tix * kTW, y0 = tiy * TH;
+    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+
+    __syncthreads();  // previous tile fully consumed (also orders the LUT fill on the first trip)
+    for (int i = tid; i < SW * SH; i += kThreads) {
+      const int sy = i / SW, sx = i - sy * SW;
+      const int gx = clampi(x0 + sx - O, 0, A.w - 1);
+      const int gy = clampi(y0 + sy - O, 0, A.h - 1);
+      const int64_t off = (int64_t)gy * A.in_sy + gx;
+      if constexpr (C == 1) {
+        s_tile[i] = __ldg(src + off);
+      } else {
+        const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
+        s_tile[i] = (KEYMODE == 2) ? rgb_luma709(c0, c1, c2) : c0;
+        s_tile[PLANE + i] = c0;
+        s_tile[2 * PLANE + i] = c1;
+        s_tile[3 * PLANE + i] = c2;
+      }
+    }
+    __syncthreads();
+
+    const int x = x0 + tx;
+#pragma unroll 1
+    for (int s = 0; s < STRIPS; ++s) {
+      const int ly0 = (s * TR + tr) * P;  // first tile row of this strip
+      const int yb = y0 + ly0;
+      if (x >= A.w || yb >= A.h) continue;
+
+      // register window: l[yy][xx] = luma at (x + xx - O, yb + yy - O)
+      float l[P + 2 * O][N];
+#pragma unroll
+      for (int yy = 0; yy < P + 2 * O; ++yy)
+#pragma unroll
+        for (int xx = 0; xx < N; ++xx) l[yy][xx] = s_tile[(ly0 + yy) * SW + tx + xx];
+
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int y = yb + p;
+        if (y >= A.h) break;
+        // window sample (i, j) with i <-> dx, j <-> dy
+        auto Wn = [&](int i, int j) { return l[p + j][i]; };
+        const int row = ravu_key<STENCIL_LITE, N, G>(A.key, Wn);
+        if (A.bucket) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
+        const float4* __restrict__ wrow = s_lut + row * LW;
+
+        if constexpr (SCALE == 2) {
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+          float hi[4], lo[4], hi2[4], lo2[4];
+          if constexpr (AR) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
+          }
+#pragma unroll
+          for (int t = 0; t <= HALF; ++t) {
+            const float4 w = wrow[t];
+            const float la = Wn(t / N, t % N);
+            r0 = fmaf(la, w.x, r0); r1 = fmaf(la, w.y, r1); r2 = fmaf(la, w.z, r2); r3 = fmaf(la, w.w, r3);
+            float lb = 0.f;
+            if (t < HALF) {
+              lb = Wn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
+              r0 = fmaf(lb, w.w, r0); r1 = fmaf(lb, w.z, r1); r2 = fmaf(lb, w.y, r2); r3 = fmaf(lb, w.x, r3);
+            }
+            if constexpr (AR) {
+              if (ar_tap<R>(t)) {
+                const float g0 = fmaxf(w.x, 0.f), g1 = fmaxf(w.y, 0.f), g2 = fmaxf(w.z, 0.f), g3 = fmaxf(w.w, 0.f);
+                {
+                  const float c = 0.1f + la, dd = 1.1f - la;
+                  const float pc = pow32(c), pd = pow32(dd);
+                  const float pc1 = pc * c, pd1 = pd * dd;
+                  hi[0] = fmaf(pc, g0, hi[0]); hi[1] = fmaf(pc, g1, hi[1]); hi[2] = fmaf(pc, g2, hi[2]); hi[3] = fmaf(pc, g3, hi[3]);
+                  lo[0] = fmaf(pd, g0, lo[0]); lo[1] = fmaf(pd, g1, lo[1]); lo[2] = fmaf(pd, g2, lo[2]); lo[3] = fmaf(pd, g3, lo[3]);
+                  hi2[0] = fmaf(pc1, g0, hi2[0]); hi2[1] = fmaf(pc1, g1, hi2[1]); hi2[2] = fmaf(pc1, g2, hi2[2]); hi2[3] = fmaf(pc1, g3, hi2[3]);
+                  lo2[0] = fmaf(pd1, g0, lo2[0]); lo2[1] = fmaf(pd1, g1, lo2[1]); lo2[2] = fmaf(pd1, g2, lo2[2]); lo2[3] = fmaf(pd1, g3, lo2[3]);
+                }
+                if (t < HALF) {
+                  const float c = 0.1f + lb, dd = 1.1f - lb;
+                  const float pc = pow32(c), pd = pow32(dd);
+                  const float pc1 = pc * c, pd1 = pd * dd;
+                  hi[0] = fmaf(pc, g3, hi[0]); hi[1] = fmaf(pc, g2, hi[1]); hi[2] = fmaf(pc, g1, hi[2]); hi[3] = fmaf(pc, g0, hi[3]);
+                  lo[0] = fmaf(pd, g3, lo[0]); lo[1] = fmaf(pd, g2, lo[1]); lo[2] = fmaf(pd, g1, lo[2]); lo[3] = fmaf(pd, g0, lo[3]);
+                  hi2[0] = fmaf(pc1, g3, hi2[0]); hi2[1] = fmaf(pc1, g2, hi2[1]); hi2[2] = fmaf(pc1, g1, hi2[2]); hi2[3] = fmaf(pc1, g0, hi2[3]);
+                  lo2[0] = fmaf(pd1, g3, lo2[0]); lo2[1] = fmaf(pd1, g2, lo2[1]); lo2[2] = fmaf(pd1, g1, lo2[2]); lo2[3] = fmaf(pd1, g0, lo2[3]);
+                }
+              }
+            }
+          }
+          float res[4] = {r0, r1, r2, r3};
+          if constexpr (AR) {
+            const float st = A.ar_strength;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float lov = 1.1f - lo2[c] / lo[c];
+              const float hiv = hi2[c] / hi[c] - 0.1f;
+              const float cl = fminf(fmaxf(res[c], lov), hiv);
+              res[c] = res[c] * (1.0f - st) + cl * st;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) res[c] = fminf(fmaxf(res[c], 0.f), 1.f);
+          }
+          // phase c -> (2x + c/2, 2y + c%2)
+          float* __restrict__ o = A.out + (int64_t)f * A.out_sn + (int64_t)(2 * y) * A.out_sy + 2 * x;
+          __stcs(reinterpret_cast<float2*>(o), make_float2(res[0], res[2]));
+          __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(res[1], res[3]));
+        } else {
+          // RAVU-3x: two texels per tap, res0 -> phases 0..3, res1 -> phases 5..8, centre copied
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            // colour sample of channel c at window tap (i, j)
+            auto Cn = [&](int i, int j) -> float {
+              if constexpr (C == 1) return l[p + j][i];
+              else return s_tile[(1 + c) * PLANE + (ly0 + p + j) * SW + tx + i];
+            };
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+            for (int t = 0; t <= HALF; ++t) {
+              const float4 w0 = wrow[2 * t], w1 = wrow[2 * t + 1];
+              const float la = Cn(t / N, t % N);
+              a0 = fmaf(la, w0.x, a0); a1 = fmaf(la, w0.y, a1); a2 = fmaf(la, w0.z, a2); a3 = fmaf(la, w0.w, a3);
+              b0 = fmaf(la, w1.x, b0); b1 = fmaf(la, w1.y, b1); b2 = fmaf(la, w1.z, b2); b3 = fmaf(la, w1.w, b3);
+              if (t < HALF) {
+                const float lb = Cn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
+                a0 = fmaf(lb, w1.w, a0); a1 = fmaf(lb, w1.z, a1); a2 = fmaf(lb, w1.y, a2); a3 = fmaf(lb, w1.x, a3);
+                b0 = fmaf(lb, w0.w, b0); b1 = fmaf(lb, w0.z, b1); b2 = fmaf(lb, w0.y, b2); b3 = fmaf(lb, w0.x, b3);
+              }
+            }
+            const float v[9] = {a0, a1, a2, a3, -1.f, b0, b1, b2, b3};
+            float* __restrict__ o =
+                A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(3 * y) * A.out_sy + 3 * x;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int i = q / 3, j = q % 3;  // imageStore(gid*3 + ivec2(i, j)): x offset i, y offset j
+              const float val = (q == 4) ? Cn(O, O) : fminf(fmaxf(v[q], 0.f), 1.f);
+              __stcs(o + (int64_t)j * A.out_sy + i, val);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C = 1, int KEYMODE = 0>
+int launch_lite(const LiteArgs& a0, int device, cudaStream_t stream) {
+  using Gm = LiteGeom<R>;
+  constexpr int LW = (SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1);
+  constexpr int ROWS = (SCALE == 2) ? 288 : 216;
+  constexpr int TH = (kThreads / kTW) * P * STRIPS;
+  constexpr int SW = kTW + 2 * Gm::O, SH = TH + 2 * Gm::O;
+  const size_t smem = sizeof(float4) * ROWS * LW + sizeof(float) * SW * SH * (C == 1 ? 1 : 4);
+  LiteArgs a = a0;
+  a.tiles_x = (a.w + kTW - 1) / kTW;
+  a.tiles_y = (a.h + TH - 1) / TH;
+  a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE>;
+  MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) {
+    set_error("ravu_lite kernel does not fit on an SM (smem %zu B)", smem);
+    return MPVP_E_UNSUPPORTED;
+  }
+  long long grid = (long long)sm_count(device) * per_sm;
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid < 1) return MPVP_OK;
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MPVP_CUDA_OK(cudaGetLastError());
+  return MPVP_OK;
+}
+
+int check_common(const mpvp_weights* lut, const mpvp_key_params* key, int radius, const void* in, const void* out,
+                 int n, int h, int w, int want_w, int want_h, int want_gauss) {
+  MPVP_REQUIRE(lut && lut->kind == 0 && lut->lut, "lut handle is null or not a LUT");
+  MPVP_REQUIRE(key, "key params are null");
+  MPVP_REQUIRE(radius >= 2 && radius <= 4, "radius %d not in {2,3,4}", radius);
+  MPVP_REQUIRE(in && out, "null frame pointer");
+  MPVP_REQUIRE(n >= 0 && h >= 1 && w >= 1, "bad frame geometry n=%d h=%d w=%d", n, h, w);
+  MPVP_REQUIRE(lut->lut_w == want_w && lut->lut_h == want_h, "LUT is %dx%d, expected %dx%d", lut->lut_w, lut->lut_h,
+               want_w, want_h);
+  MPVP_REQUIRE(key->n_gauss == want_gauss, "key params carry %d Gaussian weights, expected %d", key->n_gauss,
+               want_gauss);
+  return MPVP_OK;
+}
+
+}  // namespace
+}  // namespace mpvp
+
+using namespace mpvp;
+
+extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                                     float ar_strength, const float* in, float* out, int n, int h, int w,
+                                     int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                                     int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  const int taps = (2 * radius - 1) * (2 * radius - 1);
+  const int g = radius == 4 ? 5 : 3;
+  int rc = check_common(lut, key, radius, in, out, n, h, w, (taps + 1) / 2, 288, g * g);
+  if (rc) return rc;
+  MPVP_REQUIRE(key->n_strength == 4 && key->n_strength_thr == 3, "ravu-lite expects 3 strength thresholds");
+  MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) == 0,
+               "output rows must be 8-byte aligned (even strides)");
+  if (n == 0) return MPVP_OK;
+  DeviceGuard guard(lut->device);
+  MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
+  LiteArgs a{};
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.n = n; a.h = h; a.w = w;
+  a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;
+  a.in_sc = 0; a.out_sc = 0;
+  a.ar_strength = ar_strength;
+  a.key = *key;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (radius * 2 + (ar ? 1 : 0)) {
+    case 4: return launch_lite<2, false, 2, 4, 2>(a, lut->device, st);
+    case 5: return launch_lite<2, true, 2, 4, 2>(a, lut->device, st);
+    case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
+    case 7: return launch_lite<3, true, 2, 4, 2>(a, lut->device, st);
+    case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
+    case 9: return launch_lite<4, true, 2, 2, 4>(a, lut->device, st);
+  }
+  return MPVP_E_INVALID;
+}
+
+extern "C" int mpvp_ravu3x_launch(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                                  const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
+                                  int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
+                                  int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  const int taps = (2 * radius - 1) * (2 * radius - 1);
+  const int g = radius == 4 ? 5 : 3;
+  int rc = check_common(lut, key, radius, in, out, n, h, w, taps + 1, 216, g * g);
+  if (rc) return rc;
+  MPVP_REQUIRE(key->n_strength == 3 && key->n_strength_thr == 2, "ravu-3x expects 2 strength thresholds");
+  MPVP_REQUIRE(key_mode >= 0 && key_mode <= 2, "key_mode %d", key_mode);
+  if (n == 0) return MPVP_OK;
+  DeviceGuard guard(lut->device);
+  MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
+  LiteArgs a{};
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.n = n; a.h = h; a.w = w;
+  a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
+  a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;
+  a.key = *key;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dev = lut->device;
+  switch (radius * 3 + key_mode) {
+    case 6: return launch_lite<2, false, 3, 4, 2, 1, 0>(a, dev, st);
+    case 7: return launch_lite<2, false, 3, 4, 2, 3, 1>(a, dev, st);
+    case 8: return launch_lite<2, false, 3, 4, 2, 3, 2>(a, dev, st);
+    case 9: return launch_lite<3, false, 3, 4, 2, 1, 0>(a, dev, st);
+    case 10: return launch_lite<3, false, 3, 4, 2, 3, 1>(a, dev, st);
+    case 11: return launch_lite<3, false, 3, 4, 2, 3, 2>(a, dev, st);
+    case 12: return launch_lite<4, false, 3, 2, 4, 1, 0>(a, dev, st);
+    case 13: return launch_lite<4, false, 3, 2, 4, 3, 1>(a, dev, st);
+    case 14: return launch_lite<4, false, 3, 2, 4, 3, 2>(a, dev, st);
+  }
+  return MPVP_E_INVALID;
+}
+
+// Host-buffer convenience: H2D, kernel, D2H inside the call (frames are staged in chunks through two
+// streams so that copies of chunk k+1 overlap the kernel of chunk k when the host memory is pinned).
+extern "C" int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                                   float ar_strength, const float* host_in, float* host_out, int n, int h, int w) {
+  MPVP_REQUIRE(lut && lut->kind == 0, "lut handle is null or not a LUT");
+  MPVP_REQUIRE(host_in && host_out, "null host pointer");
+  MPVP_REQUIRE(n >= 0 && h >= 1 && w >= 1, "bad frame geometry n=%d h=%d w=%d", n, h, w);
+  if (n == 0) return MPVP_OK;
+  DeviceGuard guard(lut->device);
+  MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
+  const size_t in_frame = (size_t)h * w, out_frame = in_frame * 4;
+  const int chunk = n < 4 ? n : 4;
+  cudaStream_t st[2] = {nullptr, nullptr};
+  float* din[2] = {nullptr, nullptr};
+  float* dout[2] = {nullptr, nullptr};
+  int rc = MPVP_OK;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&din[i], chunk * in_frame * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dout[i], chunk * out_frame * sizeof(float));
+  }
+  for (int f0 = 0, k = 0; f0 < n && e == cudaSuccess && rc == MPVP_OK; f0 += chunk, ++k) {
+    const int b = k & 1, m = (n - f0) < chunk ? (n - f0) : chunk;
+    e = cudaMemcpyAsync(din[b], host_in + (size_t)f0 * in_frame, m * in_frame * sizeof(float), cudaMemcpyHostToDevice, st[b]);
+    if (e != cudaSuccess) break;
+    rc = mpvp_ravu_lite_launch(lut, key, radius, ar, ar_strength, din[b], dout[b], m, h, w, (int64_t)in_frame, w,
+                               (int64_t)out_frame, 2 * w, nullptr, st[b]);
+    if (rc != MPVP_OK) break;
+    e = cudaMemcpyAsync(host_out + (size_t)f0 * out_frame, dout[b], m * out_frame * sizeof(float), cudaMemcpyDeviceToHost, st[b]);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (st[i]) {
+      cudaError_t e2 = cudaStreamSynchronize(st[i]);
+      if (e == cudaSuccess) e = e2;
+      cudaStreamDestroy(st[i]);
+    }
+    if (din[i]) cudaFree(din[i]);
+    if (dout[i]) cudaFree(dout[i]);
+  }
+  if (rc != MPVP_OK) return rc;
+  if (e != cudaSuccess) {
+    set_error("mpvp_ravu_lite_host: %s", cudaGetErrorString(e));
+    return MPVP_E_CUDA;
+  }
+  return MPVP_OK;
+}

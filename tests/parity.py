@@ -1,0 +1,63 @@
+"""Shared parity metrics (north_star tolerances, written here once):
+
+* RAVU bucket indices must match on >= 99.99 % of key evaluations, mismatches only at quantisation
+  boundaries;
+* output max abs error <= 1e-3 on [0,1] wherever the bucket agrees, PSNR >= 60 dB overall;
+* NNEDI3 within the same bound.
+"""
+import numpy as np
+
+BUCKET_MIN_AGREE = 0.9999
+MAX_ABS = 1e-3
+MIN_PSNR = 60.0
+
+
+def psnr(a, b):
+    mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+    return 200.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+def boundary_distance(key, v):
+    """Distance of every key evaluation to the nearest quantisation boundary, in the units of each
+    quantiser (angle: sectors; strength / coherence: relative)."""
+    af = np.asarray(key.angle_f, np.float64)
+    d_angle = np.minimum(af - np.floor(af), np.ceil(af) - af)
+    d_angle = np.where(np.isnan(d_angle), 0.0, d_angle)
+    lam = np.asarray(key.lam, np.float64)
+    if v.strength_thr:
+        d_str = np.min([np.abs(lam - t) / t for t in v.strength_thr], axis=0)
+    else:
+        val = np.log2(lam * v.strength_log2_scale + 1.192092896e-7)
+        d_str = np.abs(val - np.round(val))
+    mu = np.asarray(key.mu, np.float64)
+    d_coh = np.min([np.abs(mu - t) for t in v.coherence_thr], axis=0)
+    d_coh = np.where(np.isnan(d_coh), 0.0, d_coh)
+    return np.minimum(np.minimum(d_angle, d_str), d_coh)
+
+
+def check_buckets(got_rows, key, v, what=""):
+    """got_rows, key.row: same shape.  Returns the agreement mask."""
+    same = np.asarray(got_rows) == key.row
+    frac = float(same.mean())
+    assert frac >= BUCKET_MIN_AGREE or (~same).sum() <= 1, f"{what}: bucket agreement {frac:.6f} < {BUCKET_MIN_AGREE}"
+    if not same.all():
+        dist = boundary_distance(key, v)[~same]
+        # a degenerate (flat) neighbourhood has an arbitrary angle: |b| ~ eps flips theta between 0 and atan
+        flat = np.asarray(key.lam)[~same] < 1e-3
+        assert np.all((dist < 2e-3) | flat), f"{what}: bucket mismatch away from a quantisation boundary (dist {dist.max():.3e})"
+    return same
+
+
+def check_output(got, ref, same_mask_out=None, what=""):
+    got = np.asarray(got, np.float32)
+    ref = np.asarray(ref, np.float32)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    assert np.isfinite(got).all() or not np.isfinite(ref).all(), f"{what}: non-finite output"
+    diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    diff = np.where(np.isnan(ref), 0.0, diff)
+    m = diff if same_mask_out is None else diff[same_mask_out]
+    mx = float(m.max()) if m.size else 0.0
+    assert mx <= MAX_ABS, f"{what}: max abs error {mx:.3e} > {MAX_ABS}"
+    p = psnr(np.nan_to_num(got), np.nan_to_num(ref))
+    assert p >= MIN_PSNR, f"{what}: PSNR {p:.1f} dB < {MIN_PSNR}"
+    return mx, p

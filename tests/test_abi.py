@@ -1,0 +1,65 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/mpvp.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mpvp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpvp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for want in ("mpvp_last_error", "mpvp_weights_create_lut", "mpvp_weights_create_nnedi3", "mpvp_weights_destroy",
+                 "mpvp_ravu_lite_launch", "mpvp_ravu_launch", "mpvp_ravu3x_launch", "mpvp_ravu_zoom_launch",
+                 "mpvp_nnedi3_launch", "mpvp_ravu_lite_host"):
+        assert want in names
+
+
+def test_library_builds_loads_and_exports_everything():
+    from mpv_prescalers_b200 import _native
+
+    _native.build()
+    lib = _native.lib()
+    assert lib.mpvp_abi_version() == 1
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in _declared():
+        assert hasattr(raw, name), f"libmpvp.so does not export {name}"
+    assert sorted(_native.SIGNATURES) == _declared()
+    assert lib.mpvp_last_error() is not None
+
+
+def test_struct_layout_matches_header():
+    from mpv_prescalers_b200 import _native
+
+    # float[36] + int + float[3] + int + float + int + float[2] = 45 4-byte fields
+    assert ctypes.sizeof(_native.KeyParams) == 45 * 4
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+
+    from mpv_prescalers_b200 import _native, prescale
+    from tests.conftest import hook_path
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError, match="no CPU fallback"):
+        prescale(torch.zeros(1, 16, 16), hook_path("ravu-lite-r3.hook"))
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under mpv_prescalers_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "mpv_prescalers_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"

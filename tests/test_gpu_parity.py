@@ -1,0 +1,329 @@
+"""GPU parity tests: CUDA path (through prescale() -> ctypes -> C ABI) against the oracle.
+
+Run on the B200 box with ``pytest -m gpu``.  Tolerances are the north_star's (tests/parity.py).
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import hook_path
+from tests.parity import check_buckets, check_output, psnr
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device visible: GPU tests cannot run (there is no CPU fallback)")
+    from mpv_prescalers_b200 import _native
+
+    _native.lib()  # fail loudly if the extension is missing
+
+
+def _frames(v, n, h, w, config):
+    from mpv_prescalers_b200.synth import batch
+
+    return batch(n, v.channels, h, w, config=config)
+
+
+def _oracle(v, frame, out_size=None):
+    """frame: [C,H,W] -> oracle result on [H,W] or [H,W,3]."""
+    from oracle import ravu_np
+
+    img = frame[0] if v.channels == 1 else np.moveaxis(frame, 0, -1)
+    return ravu_np.run(img, v, out_size)
+
+
+def _dilate(mask_bad, r):
+    from scipy.ndimage import binary_dilation
+
+    return binary_dilation(mask_bad, structure=np.ones((2 * r + 1, 2 * r + 1), bool))
+
+
+def _run_ravu_variant(name, n, h, w, config, out_hw=None):
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    v = hk.variant
+    x = _frames(v, n, h, w, config)
+    xt = torch.from_numpy(x).cuda()
+    if v.channels == 1:
+        xt = xt[:, 0]
+    out, bk = prescale(xt, hk, output_size=out_hw, return_buckets=True)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    bk = bk.cpu().numpy()
+    stats = []
+    for f in range(n):
+        osz = None if out_hw is None else (out_hw[1], out_hw[0])
+        ref = _oracle(v, x[f], osz)
+        got = out[f] if v.channels == 1 else np.moveaxis(out[f], 0, -1)
+        fam = v.family
+        if fam == "ravu":
+            bad = np.zeros((h, w), bool)
+            for k in range(3):
+                same = check_buckets(bk[f, k], ref.keys[k], v, f"{name} frame {f} key {k}")
+                bad |= ~same
+            ok = ~_dilate(bad, v.radius + 1) if bad.any() else ~bad
+            mask = np.repeat(np.repeat(ok, 2, 0), 2, 1)
+        else:
+            same = check_buckets(bk[f], ref.keys[0], v, f"{name} frame {f}")
+            rep = {"ravu-lite": 2, "ravu-3x": 3, "ravu-zoom": 1}[fam]
+            mask = np.repeat(np.repeat(same, rep, 0), rep, 1)
+        if got.ndim == 3:
+            mask = np.repeat(mask[..., None], 3, -1)
+        stats.append(check_output(got, ref.out, mask, f"{name} frame {f}"))
+    return stats
+
+
+RAVU_VARIANTS = (
+    [f"ravu-lite{ar}-r{r}.hook" for ar in ("", "-ar") for r in (2, 3, 4)]
+    + [f"ravu-r{r}{p}.hook" for r in (2, 3, 4) for p in ("", "-yuv", "-rgb")]
+    + [f"compute/ravu-3x-r{r}{p}.hook" for r in (2, 3, 4) for p in ("", "-yuv", "-rgb")]
+    + ["compute/ravu-lite-ar-r3.hook", "gather/ravu-lite-ar-r3.hook", "compute/ravu-r3-rgb.hook", "gather/ravu-r3.hook"]
+)
+
+
+@pytest.mark.parametrize("name", RAVU_VARIANTS)
+def test_ravu_variant_matches_oracle(name):
+    _run_ravu_variant(name, n=2, h=101, w=157, config=11)
+
+
+ZOOM_CASES = [
+    ("ravu-zoom-r2.hook", (64, 90), (192, 270)),       # exact 3x (knife-edge positions, App. D.6)
+    ("ravu-zoom-r3.hook", (64, 90), (192, 270)),
+    ("ravu-zoom-r3.hook", (57, 83), (131, 199)),       # non-integer ratio
+    ("ravu-zoom-ar-r2.hook", (64, 90), (192, 270)),
+    ("ravu-zoom-ar-r2.hook", (57, 83), (150, 197)),
+    ("ravu-zoom-ar-r2-rgb.hook", (48, 60), (109, 155)),
+    ("ravu-zoom-r2-yuv.hook", (48, 60), (96, 121)),
+]
+
+
+@pytest.mark.parametrize("name,in_hw,out_hw", ZOOM_CASES)
+def test_ravu_zoom_matches_oracle(name, in_hw, out_hw):
+    _run_ravu_variant(name, n=2, h=in_hw[0], w=in_hw[1], config=13, out_hw=out_hw)
+
+
+def test_config1_ravu_lite_r3_960x540():
+    """BASELINE.json configs[0]: ravu-lite-r3 2x luma upscale of one synthetic 960x540 plane."""
+    stats = _run_ravu_variant("ravu-lite-r3.hook", n=1, h=540, w=960, config=1)
+    assert stats[0][1] >= 60.0
+
+
+def test_config2_variant_ravu_lite_ar_r3_full_frame():
+    """The north-star variant on one full 1080p frame against the oracle."""
+    _run_ravu_variant("ravu-lite-ar-r3.hook", n=1, h=1080, w=1920, config=2)
+
+
+def test_config4_zoom_720p_crop_exact_3x():
+    _run_ravu_variant("ravu-zoom-r3.hook", n=1, h=180, w=320, config=4, out_hw=(540, 960))
+
+
+NNEDI3_VARIANTS = [
+    "nnedi3-nns16-win8x4.hook", "nnedi3-nns16-win8x6.hook", "nnedi3-nns32-win8x4.hook", "nnedi3-nns32-win8x6.hook",
+    "nnedi3-nns64-win8x4.hook", "nnedi3-nns64-win8x6.hook", "nnedi3-nns128-win8x4.hook", "nnedi3-nns128-win8x6.hook",
+    "nnedi3-nns256-win8x4.hook", "nnedi3-nns256-win8x6.hook",
+    "gather/nnedi3-nns16-win8x4.hook", "compute/nnedi3-nns16-win8x4.hook", "gather/nnedi3-nns32-win8x6.hook",
+]
+
+
+@pytest.mark.parametrize("name", NNEDI3_VARIANTS)
+def test_nnedi3_matches_oracle(name):
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import nnedi3_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    v = hk.variant
+    big = v.nns >= 128
+    n, h, w = (1, 45, 150) if big else (2, 77, 139)
+    x = batch(n, 1, h, w, config=15)
+    out = prescale(torch.from_numpy(x).cuda(), hk)
+    torch.cuda.synchronize()
+    assert out.offset == (-0.5, -0.5)
+    out = out.cpu().numpy()
+    for f in range(n):
+        ref, _ = nnedi3_np.nnedi3(x[f, 0], v)
+        check_output(out[f, 0], ref, None, f"{name} frame {f}")
+
+
+def test_nnedi3_single_axis_when():
+    """Per-axis WHEN (nnedi3-nns16-win8x4.hook:19,109): only double_y fires for a tall target."""
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import nnedi3_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("nnedi3-nns16-win8x4.hook"))
+    x = batch(1, 1, 40, 64, config=16)
+    out = prescale(torch.from_numpy(x).cuda(), hk, output_size=(80, 70))
+    assert tuple(out.shape) == (1, 1, 80, 64) and out.offset == (0.0, -0.5)
+    ref, _ = nnedi3_np.nnedi3(x[0, 0], hk.variant, double_y=True, double_x=False)
+    check_output(out.cpu().numpy()[0, 0], ref, None, "double_y only")
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+
+EDGE_SIZES = [(1, 1), (1, 9), (9, 1), (2, 3), (5, 5), (33, 65), (64, 64), (65, 129)]
+
+
+@pytest.mark.parametrize("name", ["ravu-lite-ar-r3.hook", "ravu-lite-r4.hook", "ravu-r3.hook", "ravu-r4-rgb.hook", "compute/ravu-3x-r3.hook"])
+@pytest.mark.parametrize("hw", EDGE_SIZES)
+def test_edge_sizes(name, hw):
+    _run_ravu_variant(name, n=1, h=hw[0], w=hw[1], config=17)
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (3, 2), (9, 17)])
+def test_edge_sizes_zoom_and_nnedi3(hw):
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import nnedi3_np
+
+    _run_ravu_variant("ravu-zoom-r2.hook", n=1, h=hw[0], w=hw[1], config=18, out_hw=(hw[0] * 2 + 1, hw[1] * 3))
+    hk = HookFile.parse(hook_path("nnedi3-nns16-win8x6.hook"))
+    x = batch(1, 1, hw[0], hw[1], config=19)
+    out = prescale(torch.from_numpy(x).cuda(), hk).cpu().numpy()
+    ref, _ = nnedi3_np.nnedi3(x[0, 0], hk.variant)
+    check_output(out[0, 0], ref, None, f"nnedi3 {hw}")
+
+
+@pytest.mark.parametrize("name", ["ravu-lite-r3.hook", "ravu-lite-ar-r3.hook", "ravu-r3.hook", "compute/ravu-3x-r2.hook", "nnedi3-nns32-win8x4.hook"])
+def test_pathological_planes(name):
+    """Constant, step, 1-px checkerboard, all-zeros, all-ones planes."""
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import pathological
+    from oracle import nnedi3_np, ravu_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    v = hk.variant
+    for pname, img in pathological(37, 53).items():
+        out = prescale(torch.from_numpy(img).cuda(), hk).cpu().numpy()
+        if v.family == "nnedi3":
+            ref, _ = nnedi3_np.nnedi3(img, v)
+        else:
+            ref = ravu_np.run(img, v).out
+        # degenerate planes sit exactly ON quantisation boundaries (b == 0, lambda == 0): compare values,
+        # which are bucket-independent for flat regions, with the global tolerance
+        d = np.abs(np.nan_to_num(out) - np.nan_to_num(ref))
+        if pname in ("zeros", "ones", "const"):
+            assert d.max() <= 1e-3, f"{name} {pname}: flat plane not preserved ({d.max():.3e})"
+        else:
+            assert np.mean(d > 1e-3) <= 0.02 and psnr(np.nan_to_num(out), np.nan_to_num(ref)) >= 40.0, f"{name} {pname}"
+
+
+# ---- size-independent properties at BASELINE sizes -------------------------------------------------
+
+
+def test_full_size_frame_independence_and_flat():
+    """config 2 size: a frame's result does not depend on its batch neighbours (bit-exact), and a flat frame
+    stays flat (LUT rows are partitions of unity)."""
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import torch_batch
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-ar-r3.hook"))
+    x = torch_batch(8, 1, 1080, 1920, "cuda", seed=5)
+    x[3] = 0.25
+    out = prescale(x, hk)
+    assert tuple(out.shape) == (8, 1, 2160, 3840)
+    solo = prescale(x[5:6].clone(), hk)
+    assert torch.equal(out[5:6], solo)
+    assert float((out[3] - 0.25).abs().max()) <= 1e-3
+    # strided (non-contiguous batch) input goes through the explicit strides of the C ABI
+    xs = x[::2]
+    outs = prescale(xs, hk)
+    assert torch.equal(outs, out[::2])
+
+
+def test_host_tensor_path_matches_device_path():
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-ar-r3.hook"))
+    x = torch.from_numpy(batch(5, 1, 120, 200, config=21))
+    dev = prescale(x.cuda(), hk).cpu()
+    host = prescale(x.pin_memory(), hk)
+    assert host.device.type == "cpu" and torch.equal(dev, host)
+
+
+def test_lut_precision_fp32_option():
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import ravu_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-r3.hook"))
+    x = batch(1, 1, 90, 130, config=22)
+    out = prescale(torch.from_numpy(x).cuda(), hk, lut_precision="fp32").cpu().numpy()
+    ref = ravu_np.ravu_lite(x[0, 0], hk.variant, lut_precision="fp32")
+    assert np.mean(np.abs(out[0, 0] - ref.out) > 1e-3) <= 1e-3
+
+
+def test_when_false_returns_input_unchanged():
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-ar-r3.hook"))
+    x = torch.rand(1, 1, 32, 48, device="cuda")
+    out = prescale(x, hk, output_size=(40, 60))  # ratio 0.8 > 0.707106: WHEN is false (ravu-lite-ar-r3.hook:20)
+    assert out.applied is False and out.data_ptr() == x.data_ptr()
+
+
+def test_multi_gpu_sharding_equals_single_gpu():
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    hk = HookFile.parse(hook_path("ravu-lite-ar-r3.hook"))
+    x = torch.from_numpy(batch(5, 1, 90, 160, config=23))
+    single = prescale(x.cuda(0), hk).cpu()
+    parts = prescale(x, hk, devices=[0, 1])
+    assert [p.device.index for p in parts] == [0, 1]
+    assert torch.equal(torch.cat([p.cpu() for p in parts]), single)
+
+
+def test_c_abi_host_entry_point():
+    """mpvp_ravu_lite_host: host pointers in, host pointers out."""
+    import ctypes
+
+    from mpv_prescalers_b200 import HookFile, _native, prescale
+    from mpv_prescalers_b200.api import upload_weights
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-ar-r3.hook"))
+    v = hk.variant
+    x = batch(6, 1, 50, 70, config=24)
+    W = upload_weights(hk, 0)
+    out = np.empty((6, 1, 100, 140), np.float32)
+    rc = _native.lib().mpvp_ravu_lite_host(W.handles["lut"], ctypes.byref(W.key), v.radius, 1, float(v.ar_strength),
+                                           x.ctypes.data, out.ctypes.data, 6, 50, 70)
+    _native.check(rc, "mpvp_ravu_lite_host")
+    ref = prescale(torch.from_numpy(x).cuda(), hk).cpu().numpy()
+    assert np.array_equal(out, ref)
+
+
+def test_c_abi_error_convention():
+    import ctypes
+
+    from mpv_prescalers_b200 import HookFile, _native
+    from mpv_prescalers_b200.api import upload_weights
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-r3.hook"))
+    W = upload_weights(hk, 0)
+    lib = _native.lib()
+    x = torch.zeros(1, 8, 8, device="cuda")
+    o = torch.zeros(1, 16, 16, device="cuda")
+    rc = lib.mpvp_ravu_lite_launch(W.handles["lut"], ctypes.byref(W.key), 4, 0, 0.0, x.data_ptr(), o.data_ptr(), 1, 8, 8, 64, 8, 256, 16, None, None)
+    assert rc < 0 and b"LUT is" in lib.mpvp_last_error()
+    rc = lib.mpvp_ravu_lite_launch(None, ctypes.byref(W.key), 3, 0, 0.0, x.data_ptr(), o.data_ptr(), 1, 8, 8, 64, 8, 256, 16, None, None)
+    assert rc < 0
