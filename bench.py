@@ -305,17 +305,18 @@ def main():
     if not args.no_e2e:
         xh = x.cpu().pin_memory()
         e2e_steps = max(1, min(args.steps, 3))
-        o = prescale(xh, hk, out_size)  # warm-up (allocations, pinned output pool)
+        oh_pinned = torch.empty((nf, c, oh, ow), dtype=torch.float32, pin_memory=True)
+        o = prescale(xh, hk, out_size, out=oh_pinned)  # warm-up (allocator pools, streams)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            o = prescale(xh, hk, out_size)
+            o = prescale(xh, hk, out_size, out=oh_pinned)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt = max_over_ranks(dt, dev)
         e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * 4),
                "d2h_bytes_per_step": int(o.numel() * 4), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
-        del o, xh
+        del o, xh, oh_pinned
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -15,7 +15,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmpvp.so")
-SOURCES = ["abi.cu", "ravu_lite.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu"]
+SOURCES = ["abi.cu", "ravu_lite.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

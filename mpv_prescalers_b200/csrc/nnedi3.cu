@@ -7,6 +7,8 @@
 // statement of the shader (fp32 weights, fp32 accumulation, neuron-serial softmax/elliott sums) and
 // serves (a) small neuron counts where a 128-row MMA tile cannot be filled economically and (b) as
 // the on-GPU cross-check of the tcgen05 path in nnedi3_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mpvp {
@@ -134,12 +136,24 @@ int nnedi3_simt(const mpvp_weights* nn, int direction, const float* in, float* o
                 int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y,
                 cudaStream_t st) {
   NnArgs a{};
-  a.in = in; a.out = out; a.w = nn->nn_w; a.bias = nn->nn_bias;
+  a.in = in; a.out = out; a.w = nn->nn_w; a.bias = nn->nn_bias + 2 * nn->nns;  // unscaled biases
   a.n = n; a.h = h; a.w_ = w;
   a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;
   a.nns = nn->nns;
   if (nn->win_short == 4) return direction == 0 ? launch_simt<4, 0>(a, nn->device, st) : launch_simt<4, 1>(a, nn->device, st);
   return direction == 0 ? launch_simt<6, 0>(a, nn->device, st) : launch_simt<6, 1>(a, nn->device, st);
+}
+
+int nnedi3_tc(const mpvp_weights* nn, int direction, const float* in, float* out, int n, int h, int w,
+              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, cudaStream_t st);
+
+// MPVP_NNEDI3_IMPL=simt forces the CUDA-core predictor (debugging / cross-checking); default is tcgen05.
+static bool use_simt() {
+  static const bool v = [] {
+    const char* e = getenv("MPVP_NNEDI3_IMPL");
+    return e && e[0] == 's';
+  }();
+  return v;
 }
 
 }  // namespace mpvp
@@ -159,6 +173,10 @@ extern "C" int mpvp_nnedi3_launch(const mpvp_weights* nn, int direction, const f
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(nn->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", nn->device);
-  return nnedi3_simt(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
-                     static_cast<cudaStream_t>(stream));
+  if (use_simt())
+    return nnedi3_simt(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
+                       static_cast<cudaStream_t>(stream));
+  MPVP_REQUIRE(nn->nn_b, "NNEDI3 weight set has no packed tensor-core operand");
+  return nnedi3_tc(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
+                   static_cast<cudaStream_t>(stream));
 }

@@ -1,23 +1,42 @@
-// Host-side repacking of NNEDI3 weights (placeholder layout until the tcgen05 kernel lands).
+// Host-side repacking of NNEDI3 weights for the tcgen05 kernel (nnedi3_tc.cu).
+//
+// B operand (K-major, SWIZZLE_NONE canonical layout): row n' = 2*neuron + {0: W1 * log2(e), 1: W2},
+// stored as [K/8][2*nns][8] binary16, i.e. element (n', k) at ((k/8) * 2*nns + n') * 8 + k%8.
+// In UMMA descriptor terms: core matrix = 8 rows x 16 B contiguous (SBO = 128 B between 8-row groups),
+// LBO = 2*nns*16 B between K chunks of 8 elements.  log2(e) is folded into W1 and b1 so that the
+// epilogue's exp() is a bare ex2.
 #pragma once
+#include <cuda_fp16.h>
+
+#include <cstring>
 #include <vector>
 
 namespace mpvp {
 
-// w1, w2: [nns][K]; outputs: packed B operand bytes, bias [2*nns], fp32 weights [2*nns][K]
+// w1, w2: [nns][K]; outputs: packed B operand bytes, bias [2*nns] = (b1*log2e, b2) interleaved,
+// fp32 weights [2*nns][K] (unscaled, for the CUDA-core path)
 inline void nnedi3_pack_host(const float* w1, const float* w2, const float* b1, const float* b2, int nns, int K,
                              std::vector<unsigned char>& packed, std::vector<float>& bias, std::vector<float>& wf) {
-  packed.assign(16, 0);
-  bias.resize(2 * (size_t)nns);
-  wf.resize(2 * (size_t)nns * K);
+  const float kLog2e = 1.4426950408889634f;
+  const int N = 2 * nns;
+  std::vector<__half> hb((size_t)N * K);
+  bias.resize(2 * (size_t)N);  // [0, N): tensor path (b1*log2e, b2); [N, 2N): CUDA-core path (b1, b2)
+  wf.resize((size_t)N * K);
   for (int n = 0; n < nns; ++n) {
-    bias[2 * n] = b1[n];
+    bias[2 * n] = b1[n] * kLog2e;
     bias[2 * n + 1] = b2[n];
+    bias[N + 2 * n] = b1[n];
+    bias[N + 2 * n + 1] = b2[n];
     for (int k = 0; k < K; ++k) {
-      wf[(size_t)(2 * n) * K + k] = w1[(size_t)n * K + k];
-      wf[(size_t)(2 * n + 1) * K + k] = w2[(size_t)n * K + k];
+      const float a = w1[(size_t)n * K + k], b = w2[(size_t)n * K + k];
+      wf[(size_t)(2 * n) * K + k] = a;
+      wf[(size_t)(2 * n + 1) * K + k] = b;
+      hb[((size_t)(k / 8) * N + 2 * n) * 8 + (k % 8)] = __float2half_rn(a * kLog2e);
+      hb[((size_t)(k / 8) * N + 2 * n + 1) * 8 + (k % 8)] = __float2half_rn(b);
     }
   }
+  packed.resize(hb.size() * sizeof(__half));
+  memcpy(packed.data(), hb.data(), packed.size());
 }
 
 }  // namespace mpvp

@@ -1,0 +1,356 @@
+// NNEDI3 on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// What the reference does per interpolated pixel (nnedi3-nns16-win8x4.hook:20-50): window mean / stddev,
+// 2*nns dot products of length K = 8*S against constant weights, softmax(exp) . elliott epilogue.  That is a
+// dense contraction  D[pixels x 2*nns] = A[pixels x K] . B[K x 2*nns]  with a per-row epilogue:
+//
+//   A  built by CUDA cores: (x - mean) * inv_std -> binary16, written in the UMMA canonical K-major
+//      (SWIZZLE_NONE) layout [K/8][128 rows][8 halfs]; mean removal BEFORE the fp16 rounding is what keeps
+//      the result inside the 1e-3 bound;
+//   B  [K/8][2*nns][8 halfs] binary16, resident in shared memory for the whole kernel, fetched once per CTA
+//      with one TMA bulk copy (cp.async.bulk -> mbarrier); rows interleave (W1_n * log2e, W2_n);
+//   D  fp32 in tensor memory: 128 lanes (pixels) x 128-column chunks (64 neurons), two chunks in flight
+//      per warpgroup so the MMA of chunk c+1 overlaps the epilogue of chunk c;
+//   epilogue: tcgen05.ld 32x32b (thread == pixel == TMEM lane) -> ex2, rcp, FMA running sums.
+//
+// Two independent warpgroups per CTA (128 threads each) alternate over 32x4-pixel tiles; each owns half of
+// TMEM (256 columns) and issues its own tcgen05.mma from one elected thread, so one group's MMA + A-build
+// hides under the other group's MUFU-bound epilogue.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace mpvp {
+namespace {
+
+struct NnTcArgs {
+  const float* __restrict__ in;
+  float* __restrict__ out;
+  const void* __restrict__ b_packed;  // [K/8][N][8] binary16
+  const float* __restrict__ bias;     // [N] interleaved (b1*log2e, b2)
+  int n, h, w;
+  int64_t in_sn, in_sy, out_sn, out_sy;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+};
+
+constexpr int kTileW = 32, kTileH = 4;  // 128 pixels = 128 TMEM lanes
+constexpr int kWG = 2;                  // warpgroups per CTA
+constexpr int kThreads = 128 * kWG;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wg_barrier(int wg) {
+  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B contiguous;
+// SBO = byte distance between 8-row groups, LBO = byte distance between 8-element K chunks.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int S, int DIR, int NNS>
+__global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_constant__ NnTcArgs A) {
+  constexpr int K = 8 * S;
+  constexpr int KC = K / 8;                 // 16-byte K chunks per row
+  constexpr int N = 2 * NNS;                // accumulator columns per pixel
+  constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk
+  constexpr int NCH = N / CN;
+  constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
+  constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
+  constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
+  constexpr uint32_t kBBytes = (uint32_t)K * N * 2;
+  constexpr uint32_t kABytes = (uint32_t)K * 128 * 2;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_b = smem;                               // B operand
+  unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
+  float* s_bias = reinterpret_cast<float*>(s_a + kWG * kABytes);  // [N]
+  float* s_stage = s_bias + N;                             // [kWG][SH*SW]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * SH * SW + ((kWG * SH * SW) & 1));  // [kWG][2] + 1
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + kWG * 2 + 1);
+
+  const int tid = threadIdx.x;
+  const int wg = tid >> 7;       // warpgroup
+  const int lt = tid & 127;      // pixel / TMEM lane within the tile
+  const int warp = tid >> 5;
+  const int tx = lt & 31, ty = lt >> 5;
+
+  const uint32_t mbar_b = smem_u32(s_mbar + kWG * 2);
+  if (tid == 0) {
+    for (int i = 0; i < kWG * 2; ++i) mbar_init(smem_u32(s_mbar + i), 1);
+    mbar_init(mbar_b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  for (int i = tid; i < N; i += kThreads) s_bias[i] = A.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    mbar_expect_tx(mbar_b, kBBytes);
+    bulk_g2s(smem_u32(s_b), A.b_packed, kBBytes, mbar_b);
+  }
+  const uint32_t tmem_base = *s_tmem;
+  mbar_wait(mbar_b, 0);
+
+  unsigned char* my_a = s_a + wg * kABytes;
+  float* my_stage = s_stage + wg * SH * SW;
+  const uint32_t a_addr = smem_u32(my_a), b_addr = smem_u32(s_b);
+  const uint32_t idesc = make_idesc(CN);
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t chunk_counter = 0;  // chunks issued so far by this warpgroup (selects TMEM buffer + mbarrier parity)
+
+  auto issue_chunk = [&](int c, uint32_t q) {
+    // D[128 x CN] (buffer q&1 of this warpgroup) = A[128 x K] . B[rows c*CN .. c*CN+CN-1]^T
+    const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 256 + (q & 1) * 128);
+#pragma unroll
+    for (int j = 0; j < K / 16; ++j) {
+      const uint64_t ad = make_desc(a_addr + j * 2 * (128 * 16), 128 * 16, 128);
+      const uint64_t bd = make_desc(b_addr + c * CN * 16 + j * 2 * (N * 16), N * 16, 128);
+      umma_f16(d_tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(s_mbar + wg * 2 + (q & 1)));
+  };
+
+  for (long long tile = (long long)blockIdx.x * kWG + wg; tile < A.total_tiles; tile += (long long)gridDim.x * kWG) {
+    const int tix = (int)(tile % A.tiles_x);
+    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
+    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const int x0 = tix * kTileW, y0 = tiy * kTileH;
+    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+
+    // ---- stage the source rectangle (clamp-to-edge) -------------------------------------------
+    wg_barrier(wg);  // previous tile's window reads are done
+    for (int i = lt; i < SW * SH; i += 128) {
+      const int sy = i / SW, sx = i - sy * SW;
+      const int gx = clampi(x0 + sx - OX, 0, A.w - 1), gy = clampi(y0 + sy - OY, 0, A.h - 1);
+      my_stage[i] = __ldg(src + (int64_t)gy * A.in_sy + gx);
+    }
+    wg_barrier(wg);
+
+    // ---- im2col + normalisation -> A operand ----------------------------------------------------
+    float xs[K];
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int a = k / S, b = k % S;
+      const int dx = DIR == 0 ? a : b, dy = DIR == 0 ? b : a;
+      xs[k] = my_stage[(ty + dy) * SW + tx + dx];
+      sum += xs[k];
+      sumsq = fmaf(xs[k], xs[k], sumsq);
+    }
+    const float mstd0 = sum / (float)K;
+    float mstd1 = sumsq / (float)K - mstd0 * mstd0;
+    const float mstd2 = mstd1 >= kEps ? rsqrtf(mstd1) : 0.0f;
+    mstd1 *= mstd2;
+    const float orig = xs[3 * S + (S / 2 - 1)];  // window centre: long offset 0, short offset 0
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      __half2 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = __floats2half2_rn((xs[kc * 8 + 2 * e] - mstd0) * mstd2, (xs[kc * 8 + 2 * e + 1] - mstd0) * mstd2);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
+      pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+      pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
+      pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+      *reinterpret_cast<uint4*>(my_a + kc * (128 * 16) + lt * 16) = pk;
+    }
+    fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor core (async proxy)
+    tc_fence_before();     // also orders the previous tile's tcgen05.ld before the new MMAs
+    wg_barrier(wg);
+
+    if (lt == 0) {
+      tc_fence_after();
+      issue_chunk(0, chunk_counter);
+      if (NCH > 1) issue_chunk(1, chunk_counter + 1);
+    }
+
+    // ---- epilogue -----------------------------------------------------------------------------
+    float wsum = 0.f, vsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const uint32_t q = chunk_counter + c;
+      mbar_wait(smem_u32(s_mbar + wg * 2 + (q & 1)), (q >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + lane_base + (uint32_t)(wg * 256 + (q & 1) * 128);
+#pragma unroll 1
+      for (int i = 0; i < CN / 32; ++i) {
+        float v[32];
+        tmem_ld32(d_tmem + i * 32, v);
+        const float* __restrict__ bb = s_bias + c * CN + i * 32;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float2 bias = *reinterpret_cast<const float2*>(bb + 2 * e);
+          const float s1 = ex2_approx(v[2 * e] + bias.x);
+          const float t = v[2 * e + 1] + bias.y;
+          wsum += s1;
+          vsum = fmaf(s1, __fdividef(t, 1.0f + fabsf(t)), vsum);
+        }
+      }
+      if (c + 2 < NCH) {  // this TMEM buffer is needed again for chunk c+2
+        tc_fence_before();
+        wg_barrier(wg);
+        if (lt == 0) {
+          tc_fence_after();
+          issue_chunk(c + 2, q + 2);
+        }
+      }
+    }
+    chunk_counter += NCH;
+
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < A.w && y < A.h) {
+      const float pred = fminf(fmaxf(mstd0 + 5.0f * vsum / wsum * mstd1, 0.f), 1.f);
+      float* __restrict__ o = A.out + (int64_t)f * A.out_sn;
+      if (DIR == 0) {
+        __stcs(o + (int64_t)(2 * y) * A.out_sy + x, orig);
+        __stcs(o + (int64_t)(2 * y + 1) * A.out_sy + x, pred);
+      } else {
+        __stcs(reinterpret_cast<float2*>(o + (int64_t)y * A.out_sy + 2 * x), make_float2(orig, pred));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int S, int DIR, int NNS>
+int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
+  constexpr int K = 8 * S, N = 2 * NNS;
+  constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
+  constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
+  size_t smem = (size_t)K * N * 2 + (size_t)kWG * K * 128 * 2 + sizeof(float) * (N + kWG * SH * SW + 2) + 8 * (kWG * 2 + 1) + 16;
+  // one CTA per SM: the kernel allocates all 512 TMEM columns
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  NnTcArgs a = a0;
+  a.tiles_x = (a.w + kTileW - 1) / kTileW;
+  a.tiles_y = (a.h + kTileH - 1) / kTileH;
+  a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  auto kern = nnedi3_tc_kernel<S, DIR, NNS>;
+  MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = sm_count(device);
+  const long long need = (a.total_tiles + kWG - 1) / kWG;
+  if (grid > need) grid = need;
+  if (grid < 1) return MPVP_OK;
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MPVP_CUDA_OK(cudaGetLastError());
+  return MPVP_OK;
+}
+
+template <int S, int DIR>
+int dispatch_nns(const NnTcArgs& a, int nns, int device, cudaStream_t st) {
+  switch (nns) {
+    case 16: return launch_tc<S, DIR, 16>(a, device, st);
+    case 32: return launch_tc<S, DIR, 32>(a, device, st);
+    case 64: return launch_tc<S, DIR, 64>(a, device, st);
+    case 128: return launch_tc<S, DIR, 128>(a, device, st);
+    case 256: return launch_tc<S, DIR, 256>(a, device, st);
+  }
+  set_error("nns %d unsupported", nns);
+  return MPVP_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+int nnedi3_tc(const mpvp_weights* nn, int direction, const float* in, float* out, int n, int h, int w,
+              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, cudaStream_t st) {
+  NnTcArgs a{};
+  a.in = in; a.out = out; a.b_packed = nn->nn_b; a.bias = nn->nn_bias;
+  a.n = n; a.h = h; a.w = w;
+  a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;
+  if (nn->win_short == 4)
+    return direction == 0 ? dispatch_nns<4, 0>(a, nn->nns, nn->device, st) : dispatch_nns<4, 1>(a, nn->nns, nn->device, st);
+  return direction == 0 ? dispatch_nns<6, 0>(a, nn->nns, nn->device, st) : dispatch_nns<6, 1>(a, nn->nns, nn->device, st);
+}
+
+}  // namespace mpvp

@@ -62,10 +62,17 @@ def _run_ravu_variant(name, n, h, w, config, out_hw=None):
         got = out[f] if v.channels == 1 else np.moveaxis(out[f], 0, -1)
         fam = v.family
         if fam == "ravu":
-            bad = np.zeros((h, w), bool)
-            for k in range(3):
-                same = check_buckets(bk[f, k], ref.keys[k], v, f"{name} frame {f} key {k}")
-                bad |= ~same
+            # key 0 (int11) must agree except at quantisation boundaries; a flipped int11 bucket changes the
+            # int11 VALUE there, which legitimately perturbs the step-2/3 keys and outputs that tap it
+            # (cascade), so keys 1/2 and the output are checked outside the reach of key-0 flips.
+            same0 = check_buckets(bk[f, 0], ref.keys[0], v, f"{name} frame {f} key 0")
+            reach = _dilate(~same0, v.radius + 1) if not same0.all() else ~same0
+            bad = ~same0
+            for k in (1, 2):
+                samek = bk[f, k] == ref.keys[k].row
+                check_buckets(np.where(reach, ref.keys[k].row, bk[f, k]), ref.keys[k], v, f"{name} frame {f} key {k}")
+                bad |= ~samek
+            assert bad.mean() <= 3e-4 or bad.sum() <= 3, f"{name}: {bad.mean():.2e} of pixels have a differing key"
             ok = ~_dilate(bad, v.radius + 1) if bad.any() else ~bad
             mask = np.repeat(np.repeat(ok, 2, 0), 2, 1)
         else:
