@@ -63,6 +63,13 @@ typedef struct mpvp_key_params {
   float strength_log2_scale;/* ravu: 2000.0 (ravu-r2.hook:97) */
   int32_t n_strength;       /* 4 (lite/zoom), 9 (ravu), 3 (3x) */
   float coherence_thr[2];   /* 0.25 0.5 */
+  /* The same quantisers restated on the eigenvalues so that the kernels need no sqrt / division:
+   * strength = #{i : L1 >= l1_thr[i]} with l1_thr[i] = the smallest float32 x for which the shader's
+   * strength expression evaluated on lambda = sqrt(x) reaches level i+1 (exact, found by bisection);
+   * coherence: mu >= c  <=>  L1 >= L2 * ((1+c)/(1-c))^2 = L2 * coh_ratio. */
+  float l1_thr[8];
+  int32_t n_l1_thr;
+  float coh_ratio[2];
 } mpvp_key_params;
 
 /* Key source for 3-channel planes. */

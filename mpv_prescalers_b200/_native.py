@@ -66,6 +66,9 @@ class KeyParams(ctypes.Structure):
         ("strength_log2_scale", ctypes.c_float),
         ("n_strength", ctypes.c_int32),
         ("coherence_thr", ctypes.c_float * 2),
+        ("l1_thr", ctypes.c_float * 8),
+        ("n_l1_thr", ctypes.c_int32),
+        ("coh_ratio", ctypes.c_float * 2),
     ]
 
 

@@ -136,7 +136,48 @@ def _key_params(v: Variant) -> _native.KeyParams:
     kp.strength_log2_scale = float(v.strength_log2_scale)
     kp.n_strength = int(v.n_strength)
     kp.coherence_thr[0], kp.coherence_thr[1] = (float(t) for t in v.coherence_thr)
+    thr = l1_thresholds(v)
+    for i, t in enumerate(thr):
+        kp.l1_thr[i] = float(t)
+    kp.n_l1_thr = len(thr)
+    for i, c in enumerate(v.coherence_thr):
+        kp.coh_ratio[i] = float(np.float32(((1.0 + c) / (1.0 - c)) ** 2))
     return kp
+
+
+def _strength_of_l1(v: Variant, x: np.ndarray) -> np.ndarray:
+    """The shader's strength expression (float32, op for op) as a function of the eigenvalue L1."""
+    f32 = np.float32
+    lam = np.sqrt(x.astype(f32))
+    if v.strength_thr:
+        s = np.zeros(lam.shape, np.int32)
+        for t in v.strength_thr:
+            s += lam >= f32(t)
+        return s
+    with np.errstate(divide="ignore"):
+        val = np.floor(np.log2(lam * f32(v.strength_log2_scale) + f32(1.192092896e-7)))
+    return np.clip(val, 0, v.n_strength - 1).astype(np.int32)
+
+
+def l1_thresholds(v: Variant) -> List[np.float32]:
+    """For each strength level k >= 1 the smallest positive float32 L1 whose strength is >= k.
+
+    The strength quantiser is monotone in lambda = sqrt(L1) and sqrt is correctly rounded, so the set
+    {L1 : strength(L1) >= k} is an interval [x_k, inf): comparing L1 against x_k reproduces the shader's
+    decision exactly, without taking the square root on the device.  Found by bisection over the
+    float32 bit patterns."""
+    out = []
+    for k in range(1, v.n_strength):
+        lo, hi = 0, 0x7F7FFFFF  # bit patterns of +0 and FLT_MAX
+        while lo < hi:
+            mid = (lo + hi) // 2
+            x = np.array([mid], dtype=np.uint32).view(np.float32)
+            if _strength_of_l1(v, x)[0] >= k:
+                hi = mid
+            else:
+                lo = mid + 1
+        out.append(np.array([lo], dtype=np.uint32).view(np.float32)[0])
+    return out
 
 
 def upload_weights(hook: HookFile, device: int, lut_precision: str = "fp16") -> _Weights:

@@ -158,6 +158,82 @@ __device__ __forceinline__ int ravu_key(const mpvp_key_params& kp, WF W) {
   return key_from_abd(kp, a, b, d);
 }
 
+// ---- the same key without sqrt / division / atan2 ------------------------------------------------------
+// Up to (L1, L2) the arithmetic is the shader's, op for op.  The three quantisers are then evaluated on
+// quantities that decide identically except within fp32 rounding noise of a bucket edge:
+//   strength : L1 >= l1_thr[i]              (exactly equivalent: thresholds found by bisection on the host)
+//   coherence: L1 >= L2 * ((1+c)/(1-c))^2   (<=> (sqrt L1 - sqrt L2)/(sqrt L1 + sqrt L2) >= c)
+//   angle    : sector of the direction (b, L1 - a) by octant folding + 5 slope comparisons
+//              (<=> floor(mod(atan(L1 - a, b) + pi, pi) * 24 / pi))
+// Degenerate inputs keep the shader's behaviour: |b| < eps -> angle 0; sqrt(L2 < 0) = NaN -> coherence 0;
+// sqrt L1 + sqrt L2 < eps -> coherence 0.
+template <int NTHR>
+__device__ __forceinline__ int key_from_abd_fast(const mpvp_key_params& kp, float a, float b, float d) {
+  const float T = __fadd_rn(a, d);
+  const float D = __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, b));
+  const float delta = __fsqrt_rn(fmaxf(__fsub_rn(__fmul_rn(__fmul_rn(T, T), 0.25f), D), 0.0f));
+  const float halfT = __fmul_rn(T, 0.5f);
+  const float L1 = __fadd_rn(halfT, delta);
+  const float L2 = __fsub_rn(halfT, delta);
+  int strength = 0;
+#pragma unroll
+  for (int i = 0; i < NTHR; ++i) strength += (L1 >= kp.l1_thr[i]) ? 1 : 0;
+  int coh;
+  if (L1 < 3.5e-15f || L2 < 0.0f) {
+    coh = 0;  // sqrt(L1) + sqrt(L2) <= 2 sqrt(L1) < eps, or sqrt(L2) is NaN: both comparisons are false
+  } else if (L1 < 1.5e-14f) {
+    const float s1 = __fsqrt_rn(L1), s2 = __fsqrt_rn(L2);
+    const float ssum = __fadd_rn(s1, s2);
+    const float mu = ssum < kEps ? 0.0f : __fdiv_rn(__fsub_rn(s1, s2), ssum);
+    coh = (mu >= kp.coherence_thr[0] ? 1 : 0) + (mu >= kp.coherence_thr[1] ? 1 : 0);
+  } else {
+    coh = (L1 >= L2 * kp.coh_ratio[0] ? 1 : 0) + (L1 >= L2 * kp.coh_ratio[1] ? 1 : 0);
+  }
+  int angle = 0;
+  float Y = __fsub_rn(L1, a);
+  // Y == 0 (L1 - a cancels completely on near axis-aligned edges): atan(0, b) is 0 or pi, and the shader's
+  // fp32 mod(pi + pi, pi) wraps both to theta = 0
+  if (!(fabsf(b) < kEps) && Y != 0.0f) {
+    float X = b;
+    if (Y < 0.0f) { X = -X; Y = -Y; }       // theta is taken mod pi
+    const bool neg = X < 0.0f;               // mirror about the y axis: sector s -> 23 - s
+    X = fabsf(X);
+    const bool sw = Y > X;                   // reflect about 45 degrees: sector s -> 11 - s
+    const float lo = sw ? X : Y, hi = sw ? Y : X;
+    // tan(k * pi / 24), k = 1..5
+    int s = (lo >= hi * 0.13165249758739586f ? 1 : 0) + (lo >= hi * 0.2679491924311227f ? 1 : 0) +
+            (lo >= hi * 0.41421356237309503f ? 1 : 0) + (lo >= hi * 0.5773502691896257f ? 1 : 0) +
+            (lo >= hi * 0.7673269879789602f ? 1 : 0);
+    s = sw ? 11 - s : s;
+    angle = neg ? 23 - s : s;
+  }
+  return (angle * (NTHR + 1) + strength) * 3 + coh;
+}
+
+// Full key for an N x N window; FAST selects the sqrt/atan-free quantisers.
+template <int FAMILY, int N, int G, int NTHR, bool FAST, class WF>
+__device__ __forceinline__ int ravu_key2(const mpvp_key_params& kp, WF W) {
+  if constexpr (!FAST) {
+    return ravu_key<FAMILY, N, G>(kp, W);
+  } else {
+    constexpr int O = (N - G) / 2;
+    float a = 0.0f, b = 0.0f, d = 0.0f;
+#pragma unroll
+    for (int i = O; i < O + G; ++i) {
+#pragma unroll
+      for (int j = O; j < O + G; ++j) {
+        const float gx = key_diff<FAMILY, N>(i, [&](int dd) { return W(i + dd, j); });
+        const float gy = key_diff<FAMILY, N>(j, [&](int dd) { return W(i, j + dd); });
+        const float g = kp.gauss[(i - O) * G + (j - O)];
+        a = __fadd_rn(a, __fmul_rn(__fmul_rn(gx, gx), g));
+        b = __fadd_rn(b, __fmul_rn(__fmul_rn(gx, gy), g));
+        d = __fadd_rn(d, __fmul_rn(__fmul_rn(gy, gy), g));
+      }
+    }
+    return key_from_abd_fast<NTHR>(kp, a, b, d);
+  }
+}
+
 __device__ __forceinline__ float pow32(float c) {
   c *= c; c *= c; c *= c; c *= c; c *= c;
   return c;

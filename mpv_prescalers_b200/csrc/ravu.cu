@@ -45,7 +45,7 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4
   float ks[TAPS];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) ks[t] = KS(t);
-  const int row = ravu_key<STENCIL_RAVU, N, G>(kp, [&](int i, int j) { return ks[i * N + j]; });
+  const int row = ravu_key2<STENCIL_RAVU, N, G, 8, true>(kp, [&](int i, int j) { return ks[i * N + j]; });
   const float4* __restrict__ wrow = s_lut + row * LW;
 #pragma unroll
   for (int c = 0; c < C; ++c) res[c] = 0.f;

@@ -12,6 +12,8 @@
 // gradients, and the (0.1+l)^32 / (1.1-l)^32 anti-ringing powers are computed once per source
 // pixel and reused by every output pixel that taps them.  All 4 (or 9) sub-pixel phases are
 // written interleaved with 8-byte coalesced streaming stores.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mpvp {
@@ -55,7 +57,7 @@ __device__ __forceinline__ float rgb_luma709(float r, float g, float b) {
 }
 
 // C = colour channels (1 or 3; 3 only for SCALE == 3), KEYMODE: 0 luma, 1 yuv (key = channel 0), 2 rgb
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE>
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
 __global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : 2))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
   static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
@@ -123,7 +125,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
         if (y >= A.h) break;
         // window sample (i, j) with i <-> dx, j <-> dy
         auto Wn = [&](int i, int j) { return l[p + j][i]; };
-        const int row = ravu_key<STENCIL_LITE, N, G>(A.key, Wn);
+        const int row = ravu_key2<STENCIL_LITE, N, G, (SCALE == 2 ? 3 : 2), FASTKEY>(A.key, Wn);
         if (A.bucket) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
         const float4* __restrict__ wrow = s_lut + row * LW;
 
@@ -148,22 +150,24 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
               if (ar_tap<R>(t)) {
                 const float g0 = fmaxf(w.x, 0.f), g1 = fmaxf(w.y, 0.f), g2 = fmaxf(w.z, 0.f), g3 = fmaxf(w.w, 0.f);
                 {
-                  const float c = 0.1f + la, dd = 1.1f - la;
-                  const float pc = pow32(c), pd = pow32(dd);
-                  const float pc1 = pc * c, pd1 = pd * dd;
-                  hi[0] = fmaf(pc, g0, hi[0]); hi[1] = fmaf(pc, g1, hi[1]); hi[2] = fmaf(pc, g2, hi[2]); hi[3] = fmaf(pc, g3, hi[3]);
-                  lo[0] = fmaf(pd, g0, lo[0]); lo[1] = fmaf(pd, g1, lo[1]); lo[2] = fmaf(pd, g2, lo[2]); lo[3] = fmaf(pd, g3, lo[3]);
-                  hi2[0] = fmaf(pc1, g0, hi2[0]); hi2[1] = fmaf(pc1, g1, hi2[1]); hi2[2] = fmaf(pc1, g2, hi2[2]); hi2[3] = fmaf(pc1, g3, hi2[3]);
-                  lo2[0] = fmaf(pd1, g0, lo2[0]); lo2[1] = fmaf(pd1, g1, lo2[1]); lo2[2] = fmaf(pd1, g2, lo2[2]); lo2[3] = fmaf(pd1, g3, lo2[3]);
-                }
-                if (t < HALF) {
-                  const float c = 0.1f + lb, dd = 1.1f - lb;
-                  const float pc = pow32(c), pd = pow32(dd);
-                  const float pc1 = pc * c, pd1 = pd * dd;
-                  hi[0] = fmaf(pc, g3, hi[0]); hi[1] = fmaf(pc, g2, hi[1]); hi[2] = fmaf(pc, g1, hi[2]); hi[3] = fmaf(pc, g0, hi[3]);
-                  lo[0] = fmaf(pd, g3, lo[0]); lo[1] = fmaf(pd, g2, lo[1]); lo[2] = fmaf(pd, g1, lo[2]); lo[3] = fmaf(pd, g0, lo[3]);
-                  hi2[0] = fmaf(pc1, g3, hi2[0]); hi2[1] = fmaf(pc1, g2, hi2[1]); hi2[2] = fmaf(pc1, g1, hi2[2]); hi2[3] = fmaf(pc1, g0, hi2[3]);
-                  lo2[0] = fmaf(pd1, g3, lo2[0]); lo2[1] = fmaf(pd1, g2, lo2[1]); lo2[2] = fmaf(pd1, g1, lo2[2]); lo2[3] = fmaf(pd1, g0, lo2[3]);
+                  {
+                    const float c = 0.1f + la, dd = 1.1f - la;
+                    const float pc = pow32(c), pd = pow32(dd);
+                    const float pc1 = pc * c, pd1 = pd * dd;
+                    hi[0] = fmaf(pc, g0, hi[0]); hi[1] = fmaf(pc, g1, hi[1]); hi[2] = fmaf(pc, g2, hi[2]); hi[3] = fmaf(pc, g3, hi[3]);
+                    lo[0] = fmaf(pd, g0, lo[0]); lo[1] = fmaf(pd, g1, lo[1]); lo[2] = fmaf(pd, g2, lo[2]); lo[3] = fmaf(pd, g3, lo[3]);
+                    hi2[0] = fmaf(pc1, g0, hi2[0]); hi2[1] = fmaf(pc1, g1, hi2[1]); hi2[2] = fmaf(pc1, g2, hi2[2]); hi2[3] = fmaf(pc1, g3, hi2[3]);
+                    lo2[0] = fmaf(pd1, g0, lo2[0]); lo2[1] = fmaf(pd1, g1, lo2[1]); lo2[2] = fmaf(pd1, g2, lo2[2]); lo2[3] = fmaf(pd1, g3, lo2[3]);
+                  }
+                  if (t < HALF) {
+                    const float c = 0.1f + lb, dd = 1.1f - lb;
+                    const float pc = pow32(c), pd = pow32(dd);
+                    const float pc1 = pc * c, pd1 = pd * dd;
+                    hi[0] = fmaf(pc, g3, hi[0]); hi[1] = fmaf(pc, g2, hi[1]); hi[2] = fmaf(pc, g1, hi[2]); hi[3] = fmaf(pc, g0, hi[3]);
+                    lo[0] = fmaf(pd, g3, lo[0]); lo[1] = fmaf(pd, g2, lo[1]); lo[2] = fmaf(pd, g1, lo[2]); lo[3] = fmaf(pd, g0, lo[3]);
+                    hi2[0] = fmaf(pc1, g3, hi2[0]); hi2[1] = fmaf(pc1, g2, hi2[1]); hi2[2] = fmaf(pc1, g1, hi2[2]); hi2[3] = fmaf(pc1, g0, hi2[3]);
+                    lo2[0] = fmaf(pd1, g3, lo2[0]); lo2[1] = fmaf(pd1, g2, lo2[1]); lo2[2] = fmaf(pd1, g1, lo2[2]); lo2[3] = fmaf(pd1, g0, lo2[3]);
+                  }
                 }
               }
             }
@@ -173,8 +177,8 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
             const float st = A.ar_strength;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float lov = 1.1f - lo2[c] / lo[c];
-              const float hiv = hi2[c] / hi[c] - 0.1f;
+              const float lov = 1.1f - __fdividef(lo2[c], lo[c]);
+              const float hiv = __fdividef(hi2[c], hi[c]) - 0.1f;
               const float cl = fminf(fmaxf(res[c], lov), hiv);
               res[c] = res[c] * (1.0f - st) + cl * st;
             }
@@ -224,8 +228,8 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
   }
 }
 
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C = 1, int KEYMODE = 0>
-int launch_lite(const LiteArgs& a0, int device, cudaStream_t stream) {
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
+int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   using Gm = LiteGeom<R>;
   constexpr int LW = (SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1);
   constexpr int ROWS = (SCALE == 2) ? 288 : 216;
@@ -236,7 +240,7 @@ int launch_lite(const LiteArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + TH - 1) / TH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE>;
+  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -251,6 +255,22 @@ int launch_lite(const LiteArgs& a0, int device, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;
+}
+
+// MPVP_KEY=exact selects the op-for-op key (sqrt, division, atan2f) instead of the equivalent
+// comparison form; used to A/B the two on the device.
+bool exact_key() {
+  static const bool v = [] {
+    const char* e = getenv("MPVP_KEY");
+    return e && e[0] == 'e';
+  }();
+  return v;
+}
+
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C = 1, int KEYMODE = 0>
+int launch_lite(const LiteArgs& a, int device, cudaStream_t stream) {
+  if (exact_key()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, false>(a, device, stream);
+  return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true>(a, device, stream);
 }
 
 int check_common(const mpvp_weights* lut, const mpvp_key_params* key, int radius, const void* in, const void* out,

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     float ks[TAPS];
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) ks[t] = kb[(t % N) * SWt + (t / N)];
-    const int row = ravu_key<STENCIL_RAVU, N, G>(A.key, [&](int i, int j) { return ks[i * N + j]; });
+    const int row = ravu_key2<STENCIL_RAVU, N, G, 3, true>(A.key, [&](int i, int j) { return ks[i * N + j]; });
     if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
 
     // LUT coordinates exactly as the shader forms them (ravu-zoom-r2.hook:24-31,109-112)

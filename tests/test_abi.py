@@ -39,8 +39,8 @@ def test_library_builds_loads_and_exports_everything():
 def test_struct_layout_matches_header():
     from mpv_prescalers_b200 import _native
 
-    # float[36] + int + float[3] + int + float + int + float[2] = 45 4-byte fields
-    assert ctypes.sizeof(_native.KeyParams) == 45 * 4
+    # float[36] + int + float[3] + int + float + int + float[2] + float[8] + int + float[2] = 56 4-byte fields
+    assert ctypes.sizeof(_native.KeyParams) == 56 * 4
 
 
 def test_product_path_fails_loudly_without_gpu():
