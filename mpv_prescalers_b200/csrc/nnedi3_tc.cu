@@ -9,14 +9,17 @@
 //      the result inside the 1e-3 bound;
 //   B  [K/8][2*nns][8 halfs] binary16, resident in shared memory for the whole kernel, fetched once per CTA
 //      with one TMA bulk copy (cp.async.bulk -> mbarrier); rows interleave (W1_n * log2e, W2_n);
-//   D  fp32 in tensor memory: 128 lanes (pixels) x 128-column chunks (64 neurons), two chunks in flight
-//      per warpgroup so the MMA of chunk c+1 overlaps the epilogue of chunk c;
-//   epilogue: tcgen05.ld 32x32b (thread == pixel == TMEM lane) -> ex2, rcp, FMA running sums.
+//      the biases ride along as one extra K step (A columns 1,1,1,0..; B rows bias hi/mid/lo);
+//   D  fp32 in tensor memory: 128 lanes (pixels) x 128-column chunks (64 neurons);
+//   epilogue: tcgen05.ld 32x32b (thread == pixel == TMEM lane, next load in flight while the current
+//      one is consumed) -> ex2 (MUFU), reciprocal (MUFU or two Newton steps on the FMA pipe), running sums.
 //
-// Two independent warpgroups per CTA (128 threads each) alternate over 32x4-pixel tiles; each owns half of
-// TMEM (256 columns) and issues its own tcgen05.mma from one elected thread, so one group's MMA + A-build
-// hides under the other group's MUFU-bound epilogue.
+// Four independent warpgroups per CTA (128 threads each) walk 32x4-pixel tiles; each owns a quarter of
+// TMEM (128 columns) and issues its own tcgen05.mma from one elected thread, so one group's MMA latency
+// and A-build hide under the other groups' MUFU/FMA-bound epilogues.
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -35,7 +38,7 @@ struct NnTcArgs {
 };
 
 constexpr int kTileW = 32, kTileH = 4;  // 128 pixels = 128 TMEM lanes
-constexpr int kWG = 2;                  // warpgroups per CTA
+constexpr int kWG = 4;                  // warpgroups per CTA
 constexpr int kThreads = 128 * kWG;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,8 +94,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// issue only (no wait): the caller overlaps the load with arithmetic and calls tmem_ld_wait() before use
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -103,10 +106,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B contiguous;
 // SBO = byte distance between 8-row groups, LBO = byte distance between 8-element K chunks.
@@ -129,27 +130,41 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1/u for u >= 1 on the FMA/ALU pipes: bit-trick seed (|rel err| < 0.13) + two Newton steps (< 3e-4, always
+// from below).  Keeps the MUFU pipe, the binding resource of the epilogue, for the exponentials.
+__device__ __forceinline__ float rcp_newton(float u) {
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(u));
+  r = r * fmaf(-u, r, 2.0f);
+  r = r * fmaf(-u, r, 2.0f);
+  return r;
+}
 
-template <int S, int DIR, int NNS>
+template <int S, int DIR, int NNS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_constant__ NnTcArgs A) {
-  constexpr int K = 8 * S;
-  constexpr int KC = K / 8;                 // 16-byte K chunks per row
+  constexpr int K = 8 * S;                  // window samples
+  constexpr int KX = K + 16;                // + one MMA K-step carrying the biases
+  constexpr int KC = K / 8;                 // 16-byte K chunks written per tile
   constexpr int N = 2 * NNS;                // accumulator columns per pixel
   constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk
   constexpr int NCH = N / CN;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
-  constexpr uint32_t kBBytes = (uint32_t)K * N * 2;
-  constexpr uint32_t kABytes = (uint32_t)K * 128 * 2;
+  constexpr int STG = (SW * SH + 3) & ~3;
+  constexpr uint32_t kBBytes = (uint32_t)KX * N * 2;
+  constexpr uint32_t kABytes = (uint32_t)KX * 128 * 2;
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_b = smem;                               // B operand
   unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
-  float* s_bias = reinterpret_cast<float*>(s_a + kWG * kABytes);  // [N]
-  float* s_stage = s_bias + N;                             // [kWG][SH*SW]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * SH * SW + ((kWG * SH * SW) & 1));  // [kWG][2] + 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + kWG * 2 + 1);
+  float* s_stage = reinterpret_cast<float*>(s_a + kWG * kABytes);  // [kWG][STG]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG] + 1
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + kWG + 1);
 
   const int tid = threadIdx.x;
   const int wg = tid >> 7;       // warpgroup
@@ -157,14 +172,25 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const int warp = tid >> 5;
   const int tx = lt & 31, ty = lt >> 5;
 
-  const uint32_t mbar_b = smem_u32(s_mbar + kWG * 2);
+  const uint32_t mbar_b = smem_u32(s_mbar + kWG);
   if (tid == 0) {
-    for (int i = 0; i < kWG * 2; ++i) mbar_init(smem_u32(s_mbar + i), 1);
+    for (int i = 0; i < kWG; ++i) mbar_init(smem_u32(s_mbar + i), 1);
     mbar_init(mbar_b, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
-  for (int i = tid; i < N; i += kThreads) s_bias[i] = A.bias[i];
+  unsigned char* my_a = s_a + wg * kABytes;
+  {
+    // constant tail of every A row: the bias step (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8)
+    const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
+    __half2 h0 = __halves2half2(one, one), h1 = __halves2half2(one, zero), hz = __halves2half2(zero, zero);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&hz); pk.w = pk.z;
+    *reinterpret_cast<uint4*>(my_a + KC * (128 * 16) + lt * 16) = pk;
+    pk.x = pk.y = pk.z;
+    *reinterpret_cast<uint4*>(my_a + (KC + 1) * (128 * 16) + lt * 16) = pk;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -175,23 +201,23 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const uint32_t tmem_base = *s_tmem;
   mbar_wait(mbar_b, 0);
 
-  unsigned char* my_a = s_a + wg * kABytes;
-  float* my_stage = s_stage + wg * SH * SW;
+  float* my_stage = s_stage + wg * STG;
   const uint32_t a_addr = smem_u32(my_a), b_addr = smem_u32(s_b);
   const uint32_t idesc = make_idesc(CN);
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  uint32_t chunk_counter = 0;  // chunks issued so far by this warpgroup (selects TMEM buffer + mbarrier parity)
+  const uint32_t my_mbar = smem_u32(s_mbar + wg);
+  const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
+  const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
 
-  auto issue_chunk = [&](int c, uint32_t q) {
-    // D[128 x CN] (buffer q&1 of this warpgroup) = A[128 x K] . B[rows c*CN .. c*CN+CN-1]^T
-    const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 256 + (q & 1) * 128);
+  auto issue_chunk = [&](int c) {
+    // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T
 #pragma unroll
-    for (int j = 0; j < K / 16; ++j) {
+    for (int j = 0; j < KX / 16; ++j) {
       const uint64_t ad = make_desc(a_addr + j * 2 * (128 * 16), 128 * 16, 128);
       const uint64_t bd = make_desc(b_addr + c * CN * 16 + j * 2 * (N * 16), N * 16, 128);
-      umma_f16(d_tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
+      umma_f16(d_col, ad, bd, idesc, j > 0 ? 1u : 0u);
     }
-    umma_commit(smem_u32(s_mbar + wg * 2 + (q & 1)));
+    umma_commit(my_mbar);
   };
 
   for (long long tile = (long long)blockIdx.x * kWG + wg; tile < A.total_tiles; tile += (long long)gridDim.x * kWG) {
@@ -211,77 +237,108 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     wg_barrier(wg);
 
     // ---- im2col + normalisation -> A operand ----------------------------------------------------
-    float xs[K];
-    float sum = 0.f, sumsq = 0.f;
+    float mstd0, mstd1, orig;
+    {
+      float xs[K];
+      float sum = 0.f, sumsq = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int a = k / S, b = k % S;
-      const int dx = DIR == 0 ? a : b, dy = DIR == 0 ? b : a;
-      xs[k] = my_stage[(ty + dy) * SW + tx + dx];
-      sum += xs[k];
-      sumsq = fmaf(xs[k], xs[k], sumsq);
-    }
-    const float mstd0 = sum / (float)K;
-    float mstd1 = sumsq / (float)K - mstd0 * mstd0;
-    const float mstd2 = mstd1 >= kEps ? rsqrtf(mstd1) : 0.0f;
-    mstd1 *= mstd2;
-    const float orig = xs[3 * S + (S / 2 - 1)];  // window centre: long offset 0, short offset 0
+      for (int k = 0; k < K; ++k) {
+        const int a = k / S, b = k % S;
+        const int dx = DIR == 0 ? a : b, dy = DIR == 0 ? b : a;
+        xs[k] = my_stage[(ty + dy) * SW + tx + dx];
+        sum += xs[k];
+        sumsq = fmaf(xs[k], xs[k], sumsq);
+      }
+      mstd0 = sum / (float)K;
+      mstd1 = sumsq / (float)K - mstd0 * mstd0;
+      const float mstd2 = mstd1 >= kEps ? rsqrtf(mstd1) : 0.0f;
+      mstd1 *= mstd2;
+      orig = xs[3 * S + (S / 2 - 1)];  // window centre: long offset 0, short offset 0
 #pragma unroll
-    for (int kc = 0; kc < KC; ++kc) {
-      __half2 h[4];
+      for (int kc = 0; kc < KC; ++kc) {
+        __half2 h[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        h[e] = __floats2half2_rn((xs[kc * 8 + 2 * e] - mstd0) * mstd2, (xs[kc * 8 + 2 * e + 1] - mstd0) * mstd2);
-      uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
-      pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
-      pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
-      pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-      *reinterpret_cast<uint4*>(my_a + kc * (128 * 16) + lt * 16) = pk;
+        for (int e = 0; e < 4; ++e)
+          h[e] = __floats2half2_rn((xs[kc * 8 + 2 * e] - mstd0) * mstd2, (xs[kc * 8 + 2 * e + 1] - mstd0) * mstd2);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(my_a + kc * (128 * 16) + lt * 16) = pk;
+      }
     }
     fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor core (async proxy)
-    tc_fence_before();     // also orders the previous tile's tcgen05.ld before the new MMAs
+    tc_fence_before();     // orders the previous tile's tcgen05.ld before the new MMAs
     wg_barrier(wg);
-
     if (lt == 0) {
       tc_fence_after();
-      issue_chunk(0, chunk_counter);
-      if (NCH > 1) issue_chunk(1, chunk_counter + 1);
+      issue_chunk(0);
     }
 
     // ---- epilogue -----------------------------------------------------------------------------
     float wsum = 0.f, vsum = 0.f;
+    float2 wsum2 = make_float2(0.f, 0.f), vsum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
-      const uint32_t q = chunk_counter + c;
-      mbar_wait(smem_u32(s_mbar + wg * 2 + (q & 1)), (q >> 1) & 1);
+      mbar_wait(my_mbar, phase);
+      phase ^= 1;
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + lane_base + (uint32_t)(wg * 256 + (q & 1) * 128);
-#pragma unroll 1
-      for (int i = 0; i < CN / 32; ++i) {
-        float v[32];
-        tmem_ld32(d_tmem + i * 32, v);
-        const float* __restrict__ bb = s_bias + c * CN + i * 32;
+      uint32_t va[32], vb[32];
+      tmem_ld32_issue(d_lane, va);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float2 bias = *reinterpret_cast<const float2*>(bb + 2 * e);
-          const float s1 = ex2_approx(v[2 * e] + bias.x);
-          const float t = v[2 * e + 1] + bias.y;
-          wsum += s1;
-          vsum = fmaf(s1, __fdividef(t, 1.0f + fabsf(t)), vsum);
+      for (int i = 0; i < CN / 32; ++i) {
+        uint32_t (&cur)[32] = (i & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (i & 1) ? va : vb;
+        tmem_ld_wait();
+        if (i + 1 < CN / 32) tmem_ld32_issue(d_lane + (i + 1) * 32, nxt);
+        // registers 0..15: softmax logits of 16 neurons, 16..31: their elliott inputs
+        if constexpr (EPI == 2) {
+          // packed f32x2: two neurons per instruction on the FMA pipe
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float2 s1, t, a, r;
+            s1.x = ex2_approx(__uint_as_float(cur[2 * e]));
+            s1.y = ex2_approx(__uint_as_float(cur[2 * e + 1]));
+            t.x = __uint_as_float(cur[16 + 2 * e]);
+            t.y = __uint_as_float(cur[16 + 2 * e + 1]);
+            a.x = fabsf(t.x);
+            a.y = fabsf(t.y);
+            const float2 nu = __ffma2_rn(a, make_float2(-1.f, -1.f), make_float2(-1.f, -1.f));  // -(1 + |t|)
+            // seed for 1/u from the bits of -u: magic - (bits & 0x7fffffff) == (magic + 0x80000000) - bits
+            r.x = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(nu.x));
+            r.y = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(nu.y));
+            r = __fmul2_rn(r, __ffma2_rn(nu, r, make_float2(2.f, 2.f)));
+            r = __fmul2_rn(r, __ffma2_rn(nu, r, make_float2(2.f, 2.f)));
+            wsum2 = __fadd2_rn(wsum2, s1);
+            vsum2 = __ffma2_rn(__fmul2_rn(s1, t), r, vsum2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float s1 = ex2_approx(__uint_as_float(cur[e]));
+            const float t = __uint_as_float(cur[16 + e]);
+            const float u = 1.0f + fabsf(t);
+            const float r = (EPI == 0) ? rcp_approx(u) : rcp_newton(u);
+            wsum += s1;
+            vsum = fmaf(s1 * t, r, vsum);
+          }
         }
       }
-      if (c + 2 < NCH) {  // this TMEM buffer is needed again for chunk c+2
+      if (c + 1 < NCH) {  // the TMEM columns are free again: next chunk of neurons
         tc_fence_before();
         wg_barrier(wg);
         if (lt == 0) {
           tc_fence_after();
-          issue_chunk(c + 2, q + 2);
+          issue_chunk(c + 1);
         }
       }
     }
-    chunk_counter += NCH;
 
+    if constexpr (EPI == 2) {
+      wsum = wsum2.x + wsum2.y;
+      vsum = vsum2.x + vsum2.y;
+    }
     const int x = x0 + tx, y = y0 + ty;
     if (x < A.w && y < A.h) {
       const float pred = fminf(fmaxf(mstd0 + 5.0f * vsum / wsum * mstd1, 0.f), 1.f);
@@ -303,19 +360,31 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   }
 }
 
+// Epilogue variants (A/B switch MPVP_NNEDI3_EPI): 0 = reciprocal on the MUFU pipe, 1 = scalar Newton
+// reciprocal on the FMA pipe, 2 (default) = Newton in packed f32x2 arithmetic (two neurons per instruction).
+static int epi_mode() {
+  static const int v = [] {
+    const char* e = getenv("MPVP_NNEDI3_EPI");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }();
+  return v;
+}
+
 template <int S, int DIR, int NNS>
 int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
-  constexpr int K = 8 * S, N = 2 * NNS;
+  constexpr int K = 8 * S, KX = K + 16, N = 2 * NNS;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
-  size_t smem = (size_t)K * N * 2 + (size_t)kWG * K * 128 * 2 + sizeof(float) * (N + kWG * SH * SW + 2) + 8 * (kWG * 2 + 1) + 16;
+  constexpr int STG = (SW * SH + 3) & ~3;
+  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (kWG + 1) + 16;
   // one CTA per SM: the kernel allocates all 512 TMEM columns
   if (smem < 120 * 1024) smem = 120 * 1024;
   NnTcArgs a = a0;
   a.tiles_x = (a.w + kTileW - 1) / kTileW;
   a.tiles_y = (a.h + kTileH - 1) / kTileH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = nnedi3_tc_kernel<S, DIR, NNS>;
+  const int mode = epi_mode();
+  auto kern = mode == 0 ? nnedi3_tc_kernel<S, DIR, NNS, 0> : (mode == 1 ? nnedi3_tc_kernel<S, DIR, NNS, 1> : nnedi3_tc_kernel<S, DIR, NNS, 2>);
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = sm_count(device);
   const long long need = (a.total_tiles + kWG - 1) / kWG;
