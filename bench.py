@@ -45,45 +45,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), sampled in-process through
+    NVML every few milliseconds (a fresh `nvidia-smi` per sample is too slow for a 40 ms region)."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.stop_flag, self.th = index, [], threading.Event(), None
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
+        nv = self.nv
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(",")])
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(reasons)))
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.002)
 
     def start(self):
+        if self.nv is None:
+            return
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 
     def stop(self):
         self.stop_flag.set()
         if self.th:
-            self.th.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-                for nm, val in zip(names, s[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            self.th.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        nv = self.nv
+        bits = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        sm = sorted(s[0] for s in self.samples)
+        seen = 0
+        for _, r in self.samples:
+            seen |= r
+        reasons = sorted(k for k, b in bits.items() if seen & b)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def algorithmic_work(wl, n_frames):
@@ -172,7 +188,7 @@ def cpu_baseline(wl, budget_s=20.0, procs=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ravu-lite-ar-r3", choices=sorted(WORKLOADS))
