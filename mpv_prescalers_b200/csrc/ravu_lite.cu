@@ -122,11 +122,12 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const int y = yb + p;
-        if (y >= A.h) break;
+        const bool live = y < A.h;  // rows past the image are computed (from clamped data) but not stored,
+                                    // so the P pixels of a strip form one basic block for the scheduler
         // window sample (i, j) with i <-> dx, j <-> dy
         auto Wn = [&](int i, int j) { return l[p + j][i]; };
         const int row = ravu_key2<STENCIL_LITE, N, G, (SCALE == 2 ? 3 : 2), FASTKEY>(A.key, Wn);
-        if (A.bucket) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
+        if (A.bucket && live) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
         const float4* __restrict__ wrow = s_lut + row * LW;
 
         if constexpr (SCALE == 2) {
@@ -188,8 +189,10 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
           }
           // phase c -> (2x + c/2, 2y + c%2)
           float* __restrict__ o = A.out + (int64_t)f * A.out_sn + (int64_t)(2 * y) * A.out_sy + 2 * x;
-          __stcs(reinterpret_cast<float2*>(o), make_float2(res[0], res[2]));
-          __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(res[1], res[3]));
+          if (live) {
+            __stcs(reinterpret_cast<float2*>(o), make_float2(res[0], res[2]));
+            __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(res[1], res[3]));
+          }
         } else {
           // RAVU-3x: two texels per tap, res0 -> phases 0..3, res1 -> phases 5..8, centre copied
 #pragma unroll
@@ -219,7 +222,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
             for (int q = 0; q < 9; ++q) {
               const int i = q / 3, j = q % 3;  // imageStore(gid*3 + ivec2(i, j)): x offset i, y offset j
               const float val = (q == 4) ? Cn(O, O) : fminf(fmaxf(v[q], 0.f), 1.f);
-              __stcs(o + (int64_t)j * A.out_sy + i, val);
+              if (live) __stcs(o + (int64_t)j * A.out_sy + i, val);
             }
           }
         }
