@@ -40,20 +40,37 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into ``libmpvp.so`` (nvcc cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a into ``libmpvp.so`` (nvcc cross-compiles without a GPU).
+
+    Each translation unit is compiled to an object in parallel (build/obj), then linked."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise NativeError("nvcc not found; cannot build libmpvp.so")
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(HERE, "..", "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        proc = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        return src, obj, proc
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    for src, _, proc in results:
+        if proc.returncode != 0:
+            raise NativeError(f"nvcc failed on {src}:\n" + proc.stdout + proc.stderr)
+        if verbose:
+            print(proc.stderr)
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources() + ["-lcuda"]
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise NativeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    link = subprocess.run([nvcc, "-shared", "-o", tmp] + [o for _, o, _ in results] + ["-lcuda"], capture_output=True, text=True)
+    if link.returncode != 0:
+        raise NativeError("link failed:\n" + link.stdout + link.stderr)
     os.replace(tmp, LIB_PATH)
-    if verbose:
-        print(proc.stderr)
     return LIB_PATH
 
 

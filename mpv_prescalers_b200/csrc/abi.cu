@@ -67,23 +67,11 @@ extern "C" int mpvp_weights_create_lut(int device, const float* host, int w, int
   W->lut_h = h;
   cudaError_t e = cudaMalloc(&W->lut, count * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(W->lut, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice);
-  // 2-D float4 array + LINEAR/clamp texture object (used by ravu-zoom's FILTER LINEAR fetches)
-  cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
-  if (e == cudaSuccess) e = cudaMallocArray(&W->tex_array, &cd, w, h);
-  if (e == cudaSuccess)
-    e = cudaMemcpy2DToArray(W->tex_array, 0, 0, tmp.data(), (size_t)w * 16, (size_t)w * 16, h, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    cudaResourceDesc rd;
-    memset(&rd, 0, sizeof(rd));
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = W->tex_array;
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof(td));
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    e = cudaCreateTextureObject(&W->tex, &rd, &td, nullptr);
+  if (e == cudaSuccess && round_to_fp16) {
+    std::vector<__half> hv(count);
+    for (size_t i = 0; i < count; ++i) hv[i] = __float2half_rn(tmp[i]);
+    e = cudaMalloc(&W->lut_half, count * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMemcpy(W->lut_half, hv.data(), count * sizeof(__half), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     set_error("LUT upload failed: %s", cudaGetErrorString(e));
@@ -135,9 +123,8 @@ extern "C" int mpvp_weights_create_nnedi3(int device, const float* w1, const flo
 extern "C" int mpvp_weights_destroy(mpvp_weights* W) {
   if (!W) return MPVP_OK;
   DeviceGuard guard(W->device);
-  if (W->tex) cudaDestroyTextureObject(W->tex);
-  if (W->tex_array) cudaFreeArray(W->tex_array);
   if (W->lut) cudaFree(W->lut);
+  if (W->lut_half) cudaFree(W->lut_half);
   if (W->nn_b) cudaFree(W->nn_b);
   if (W->nn_bias) cudaFree(W->nn_bias);
   if (W->nn_w) cudaFree(W->nn_w);

@@ -56,9 +56,8 @@ struct mpvp_weights {
   int kind = 0;  // 0 = LUT, 1 = NNEDI3
   // LUT: rows x texels_per_row float4 (values already rounded to fp16 precision if requested)
   float* lut = nullptr;
+  void* lut_half = nullptr;  // same texels as 4 x binary16 (exact when the LUT was rounded to fp16): halves L2 traffic
   int lut_w = 0, lut_h = 0;
-  cudaTextureObject_t tex = 0;  // zoom: float4 2-D array texture, LINEAR, clamp
-  cudaArray_t tex_array = nullptr;
   // NNEDI3
   int nns = 0, win_short = 0;
   void* nn_b = nullptr;     // packed fp16 B operand(s) for tcgen05
@@ -80,6 +79,17 @@ constexpr float kPi = 3.141592653589793f;
 
 enum Stencil { STENCIL_LITE = 0, STENCIL_RAVU = 1 };
 
+// Correctly rounded x / 12 in three FMA-pipe instructions instead of the generic IEEE division sequence:
+// q = x * fl(1/12); r = x - 12 q (exact, one FMA); q' = q + r * fl(1/12).  Verified equal to the correctly
+// rounded quotient for all 2^24 mantissas; the 4th-order stencil needs the *rounded* /12
+// of the shader, a bare multiplication by 1/12 flips buckets.
+__device__ __forceinline__ float div12_rn(float x) {
+  const float z = 0.0833333358168602f;
+  const float q = __fmul_rn(x, z);
+  const float r = __fmaf_rn(-q, 12.0f, x);
+  return __fmaf_rn(r, z, q);
+}
+
 // One finite difference along an axis; S(d) returns the sample at offset d along that axis.
 template <int FAMILY, int N, class SF>
 __device__ __forceinline__ float key_diff(int k, SF S) {
@@ -88,7 +98,7 @@ __device__ __forceinline__ float key_diff(int k, SF S) {
     float t = __fadd_rn(-S(2), __fmul_rn(8.0f, S(1)));
     t = __fsub_rn(t, __fmul_rn(8.0f, S(-1)));
     t = __fadd_rn(t, S(-2));
-    return __fdiv_rn(t, 12.0f);
+    return div12_rn(t);
   }
   if (k - 1 >= 0 && k + 1 <= N - 1) return __fmul_rn(__fsub_rn(S(1), S(-1)), 0.5f);
   if (k - 1 < 0) return __fsub_rn(S(1), S(0));

@@ -9,6 +9,8 @@
 // because the hook only runs when upscaling) is staged in shared memory with clamp-to-edge.  The LUT
 // ([288*9][B*9] float4, FILTER LINEAR) stays in global memory / L2 and is fetched with an explicit
 // fp32 bilinear blend of four texels, at the same texel coordinates the GL sampler would use.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mpvp {
@@ -17,8 +19,8 @@ namespace {
 struct ZoomArgs {
   const float* __restrict__ in;
   float* __restrict__ out;
-  const float4* __restrict__ lut;
-  const float4* __restrict__ lut_ar;
+  const void* __restrict__ lut;     // float4 texels, or 4 x binary16 texels (LUTH)
+  const void* __restrict__ lut_ar;
   int32_t* __restrict__ bucket;  // [n][oh][ow] or null
   int n, h, w, oh, ow;
   int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
@@ -28,7 +30,7 @@ struct ZoomArgs {
   mpvp_key_params key;
 };
 
-constexpr int kTOW = 32, kTOH = 8, kNT = kTOW * kTOH;
+constexpr int kTOW = 32, kTOH = 32, kNT = 256;  // output tile; each thread owns one column and kTOH/8 rows
 
 // Canonical position arithmetic: base texel index and sub-pixel phase of output coordinate o.
 __device__ __forceinline__ void zoom_pos(int o, int O, int I, int& base, float& sub) {
@@ -45,48 +47,58 @@ __device__ __forceinline__ float lutpos9(float x) {
   return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, x)), __fmul_rn(b, x));
 }
 
-struct Bilerp {
-  int x0, x1, y0, y1;
-  float fu, fv;
+// Per output column (or row): everything that depends on one coordinate only.  The GL LINEAR fetch at
+// normalised coordinate c of an axis with `size` texels reads texels floor(c*size - 0.5) and +1 with weight
+// frac(c*size - 0.5); inside a 9-texel LUT block that is i0 = floor(8 s) and f = frac(8 s) for the direct
+// half of the taps (sub-pixel phase s) and the same at 1 - s for the mirrored half (ravu-zoom-r2.hook:24-31).
+struct AxisEntry {
+  int base;        // source texel index of window tap 0 minus the tile origin (filled by the caller)
+  int i0, i0m;     // first LUT texel inside the 9-texel block: direct / mirrored
+  float f, fm;     // blend weight of texel i0+1: direct / mirrored
 };
 
-// GL LINEAR + clamp-to-edge at normalised coordinate (cx, cy) of a (w x h) texture.
-__device__ __forceinline__ Bilerp make_bilerp(float cx, float cy, int w, int h) {
-  const float u = __fsub_rn(__fmul_rn(cx, (float)w), 0.5f);
-  const float v = __fsub_rn(__fmul_rn(cy, (float)h), 0.5f);
-  const float u0 = floorf(u), v0 = floorf(v);
-  Bilerp b;
-  b.fu = __fsub_rn(u, u0);
-  b.fv = __fsub_rn(v, v0);
-  b.x0 = clampi((int)u0, 0, w - 1);
-  b.x1 = clampi((int)u0 + 1, 0, w - 1);
-  b.y0 = clampi((int)v0, 0, h - 1);
-  b.y1 = clampi((int)v0 + 1, 0, h - 1);
-  return b;
+__device__ __forceinline__ AxisEntry axis_entry(int o, int O, int I, int groups) {
+  // groups = number of 9-texel blocks along this LUT axis (B for x, 288 rows for y)
+  AxisEntry e;
+  float sub;
+  zoom_pos(o, O, I, e.base, sub);
+  const float p = lutpos9(sub), ip = __fsub_rn(1.0f, p);
+  // the shader divides by `groups` to normalise and the sampler multiplies by groups*9 again
+  const float u = __fsub_rn(__fmul_rn(__fdiv_rn(p, (float)groups), (float)(groups * 9)), 0.5f);
+  const float um = __fsub_rn(__fmul_rn(__fdiv_rn(ip, (float)groups), (float)(groups * 9)), 0.5f);
+  const float u0 = floorf(u), um0 = floorf(um);
+  e.i0 = (int)u0; e.f = __fsub_rn(u, u0);
+  e.i0m = (int)um0; e.fm = __fsub_rn(um, um0);
+  return e;
 }
 
-__device__ __forceinline__ float4 fetch_bilerp(const float4* __restrict__ lut, int lw, const Bilerp& b) {
-  const float4 t00 = __ldg(lut + (int64_t)b.y0 * lw + b.x0), t10 = __ldg(lut + (int64_t)b.y0 * lw + b.x1);
-  const float4 t01 = __ldg(lut + (int64_t)b.y1 * lw + b.x0), t11 = __ldg(lut + (int64_t)b.y1 * lw + b.x1);
-  const float gu = 1.0f - b.fu, gv = 1.0f - b.fv;
-  float4 r;
-  r.x = (t00.x * gu + t10.x * b.fu) * gv + (t01.x * gu + t11.x * b.fu) * b.fv;
-  r.y = (t00.y * gu + t10.y * b.fu) * gv + (t01.y * gu + t11.y * b.fu) * b.fv;
-  r.z = (t00.z * gu + t10.z * b.fu) * gv + (t01.z * gu + t11.z * b.fu) * b.fv;
-  r.w = (t00.w * gu + t10.w * b.fu) * gv + (t01.w * gu + t11.w * b.fu) * b.fv;
-  return r;
+// one LUT texel as float4, from fp32 or binary16 storage
+template <bool LUTH>
+__device__ __forceinline__ float4 lut_texel(const void* __restrict__ lut, int idx) {
+  if constexpr (LUTH) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(lut) + idx);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return __ldg(reinterpret_cast<const float4*>(lut) + idx);
+  }
 }
 
-template <int R, int C, int KEYMODE, bool AR>
+template <int R, int C, int KEYMODE, bool AR, bool LUTH>
 __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ ZoomArgs A) {
   constexpr int N = 2 * R, TAPS = N * N, G = 4;
   constexpr int B = (TAPS / 2 + 3) / 4;   // LUT blocks per row group (2 for r2, 5 for r3)
   constexpr int LWt = B * 9, LHt = 288 * 9;
-  constexpr int SWt = kTOW + 2 * R + 2, SHt = kTOH + 2 * R + 2;
+  constexpr int CW = kTOW + 2, CH = kTOH + 2;          // source cells a tile can touch (the hook only upscales)
+  constexpr int SWt = CW + N - 1, SHt = CH + N - 1;    // staged source rectangle
   constexpr int PLANE = SWt * SHt;
-  constexpr int NP = (C == 1) ? 1 : 4;  // plane 0 = key plane, 1..3 = colours
+  constexpr int NP = (C == 1) ? 1 : 4;                 // plane 0 = key plane, 1..3 = colours
+  constexpr int RPT = kTOH / (kNT / kTOW);             // rows per thread
 
   __shared__ float s_src[NP * PLANE];
+  __shared__ int s_key[CW * CH];
+  __shared__ AxisEntry s_ax[kTOW], s_ay[kTOH];
 
   const int tid = threadIdx.x;
   const int tx = tid % kTOW, ty = tid / kTOW;
@@ -98,120 +110,147 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     const int ox0 = tix * kTOW, oy0 = tiy * kTOH;
     const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
 
-    int bx_first, by_first;
+    int bx_first, by_first, bx_last, by_last;
     float dummy;
     zoom_pos(ox0, A.ow, A.w, bx_first, dummy);
     zoom_pos(oy0, A.oh, A.h, by_first, dummy);
+    zoom_pos(min(ox0 + kTOW, A.ow) - 1, A.ow, A.w, bx_last, dummy);
+    zoom_pos(min(oy0 + kTOH, A.oh) - 1, A.oh, A.h, by_last, dummy);
+    const int ncx = bx_last - bx_first + 1, ncy = by_last - by_first + 1;   // cells touched (<= CW, CH)
     const int sx0 = bx_first - (R - 1), sy0 = by_first - (R - 1);
 
     __syncthreads();
-    for (int i = tid; i < PLANE; i += kNT) {
-      const int sy = i / SWt, sx = i - sy * SWt;
+    // ---- per-axis tables -------------------------------------------------------------------------
+    if (tid < kTOW) {
+      AxisEntry e = axis_entry(min(ox0 + tid, A.ow - 1), A.ow, A.w, B);
+      e.base -= bx_first;
+      s_ax[tid] = e;
+    } else if (tid < kTOW + kTOH) {
+      AxisEntry e = axis_entry(min(oy0 + tid - kTOW, A.oh - 1), A.oh, A.h, 288);
+      e.base -= by_first;
+      s_ay[tid - kTOW] = e;
+    }
+    // ---- stage the source rectangle (clamp-to-edge) ------------------------------------------------
+    const int need_w = ncx + N - 1, need_h = ncy + N - 1;
+    for (int i = tid; i < need_w * need_h; i += kNT) {
+      const int sy = i / need_w, sx = i - sy * need_w;
       const int gx = clampi(sx0 + sx, 0, A.w - 1), gy = clampi(sy0 + sy, 0, A.h - 1);
       const int64_t off = (int64_t)gy * A.in_sy + gx;
+      const int d = sy * SWt + sx;
       if constexpr (C == 1) {
-        s_src[i] = __ldg(src + off);
+        s_src[d] = __ldg(src + off);
       } else {
         const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
-        s_src[i] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
-        s_src[PLANE + i] = c0;
-        s_src[2 * PLANE + i] = c1;
-        s_src[3 * PLANE + i] = c2;
+        s_src[d] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
+        s_src[PLANE + d] = c0;
+        s_src[2 * PLANE + d] = c1;
+        s_src[3 * PLANE + d] = c2;
       }
     }
     __syncthreads();
-
-    const int ox = ox0 + tx, oy = oy0 + ty;
-    if (ox >= A.ow || oy >= A.oh) continue;
-    int bx, by;
-    float subx, suby;
-    zoom_pos(ox, A.ow, A.w, bx, subx);
-    zoom_pos(oy, A.oh, A.h, by, suby);
-    const float* __restrict__ kb = s_src + (by - by_first) * SWt + (bx - bx_first);  // tap (0,0)
-
-    float ks[TAPS];
+    // ---- one key per source cell: every output pixel whose base texel coincides shares window and bucket ----
+    for (int i = tid; i < ncx * ncy; i += kNT) {
+      const int cy = i / ncx, cx = i - cy * ncx;
+      const float* __restrict__ kb = s_src + cy * SWt + cx;
+      float ks[TAPS];
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) ks[t] = kb[(t % N) * SWt + (t / N)];
-    const int row = ravu_key2<STENCIL_RAVU, N, G, 3, true>(A.key, [&](int i, int j) { return ks[i * N + j]; });
-    if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
+      for (int t = 0; t < TAPS; ++t) ks[t] = kb[(t % N) * SWt + (t / N)];
+      s_key[cy * CW + cx] = ravu_key2<STENCIL_RAVU, N, G, 3, true>(A.key, [&](int ii, int jj) { return ks[ii * N + jj]; });
+    }
+    __syncthreads();
 
-    // LUT coordinates exactly as the shader forms them (ravu-zoom-r2.hook:24-31,109-112)
-    const float px = lutpos9(subx), py = lutpos9(suby);
-    const float ipx = __fsub_rn(1.0f, px), ipy = __fsub_rn(1.0f, py);
-    const float spx = __fdiv_rn(px, (float)B), sipx = __fdiv_rn(ipx, (float)B);
-    const float spy = __fdiv_rn(py, 288.0f), sipy = __fdiv_rn(ipy, 288.0f);
-    const float coord_y = __fdiv_rn((float)row, 288.0f);
+    const int ox = ox0 + tx;
+    if (ox >= A.ow) continue;
+    const AxisEntry ex = s_ax[tx];
+#pragma unroll 1
+    for (int rr = 0; rr < RPT; ++rr) {
+      const int ly = ty + rr * (kNT / kTOW);
+      const int oy = oy0 + ly;
+      if (oy >= A.oh) break;
+      const AxisEntry ey = s_ay[ly];
+      const int row = s_key[ey.base * CW + ex.base];
+      if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
+      const float* __restrict__ kb = s_src + ey.base * SWt + ex.base;  // window tap (0,0)
 
-    float res[C];
-    float hi[C], lo[C], hi2[C], lo2[C];
+      float res[C];
+      float hi[C], lo[C], hi2[C], lo2[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) res[c] = hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
-
-    auto sample = [&](int c, int t) -> float {
-      if constexpr (C == 1) return ks[t];
-      else return kb[(1 + c) * PLANE + (t % N) * SWt + (t / N)];
-    };
+      for (int c = 0; c < C; ++c) res[c] = hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
 
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < 2; ++m) {
+        // LUT rows: row*9 + i0 (+1), clamp-to-edge on the whole texture like the GL sampler
+        const int yi = row * 9 + (m ? ey.i0m : ey.i0);
+        const int y0 = clampi(yi, 0, LHt - 1), y1 = clampi(yi + 1, 0, LHt - 1);
+        const float fv = m ? ey.fm : ey.f, fu = m ? ex.fm : ex.f;
+        const float w00 = (1.0f - fu) * (1.0f - fv), w10 = fu * (1.0f - fv), w01 = (1.0f - fu) * fv, w11 = fu * fv;
+        const int xi = m ? ex.i0m : ex.i0;
 #pragma unroll
-      for (int blk = 0; blk < B; ++blk) {
-        const float blkx = (float)((double)blk / (double)B);  // the literal 0.0 / 0.2 / 0.4 ... of the shader
-        const float cx = __fadd_rn(blkx, m ? sipx : spx);
-        const float cy = __fadd_rn(coord_y, m ? sipy : spy);
-        const Bilerp bl = make_bilerp(cx, cy, LWt, LHt);
-        const float4 w4 = fetch_bilerp(A.lut, LWt, bl);
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        float av[4] = {0.f, 0.f, 0.f, 0.f};
-        if constexpr (AR) {
-          const float4 a4 = fetch_bilerp(A.lut_ar, LWt, bl);
-          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-        }
+        for (int blk = 0; blk < B; ++blk) {
+          const int x0 = clampi(blk * 9 + xi, 0, LWt - 1), x1 = clampi(blk * 9 + xi + 1, 0, LWt - 1);
+          auto fetch = [&](const void* __restrict__ lut) {
+            const float4 t00 = lut_texel<LUTH>(lut, y0 * LWt + x0), t10 = lut_texel<LUTH>(lut, y0 * LWt + x1);
+            const float4 t01 = lut_texel<LUTH>(lut, y1 * LWt + x0), t11 = lut_texel<LUTH>(lut, y1 * LWt + x1);
+            float4 r;
+            r.x = t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+            r.y = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+            r.z = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+            r.w = t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+            return r;
+          };
+          const float4 w4 = fetch(A.lut);
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          float av[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (AR) {
+            const float4 a4 = fetch(A.lut_ar);
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = blk * 4 + e;
-          if (k < TAPS / 2) {
-            const int t = m ? (TAPS - 1 - k) : k;
+          for (int e = 0; e < 4; ++e) {
+            const int k = blk * 4 + e;
+            if (k < TAPS / 2) {
+              const int t = m ? (TAPS - 1 - k) : k;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const float s = sample(c, t);
-              res[c] = fmaf(s, wv[e], res[c]);
-              if constexpr (AR) {
-                const float cc = 0.1f + s, dd = 1.1f - s;
-                const float pc = pow32(cc), pd = pow32(dd);
-                hi[c] = fmaf(pc, av[e], hi[c]);
-                lo[c] = fmaf(pd, av[e], lo[c]);
-                hi2[c] = fmaf(pc * cc, av[e], hi2[c]);
-                lo2[c] = fmaf(pd * dd, av[e], lo2[c]);
+              for (int c = 0; c < C; ++c) {
+                const float s = kb[(C == 1 ? 0 : (1 + c)) * PLANE + (t % N) * SWt + (t / N)];
+                res[c] = fmaf(s, wv[e], res[c]);
+                if constexpr (AR) {
+                  const float cc = 0.1f + s, dd = 1.1f - s;
+                  const float pc = pow32(cc), pd = pow32(dd);
+                  hi[c] = fmaf(pc, av[e], hi[c]);
+                  lo[c] = fmaf(pd, av[e], lo[c]);
+                  hi2[c] = fmaf(pc * cc, av[e], hi2[c]);
+                  lo2[c] = fmaf(pd * dd, av[e], lo2[c]);
+                }
               }
             }
           }
         }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float r = res[c];
-      if constexpr (AR) {
-        const float hiv = hi2[c] / hi[c] - 0.1f;
-        const float lov = 1.1f - lo2[c] / lo[c];
-        const float cl = fminf(fmaxf(r, lov), hiv);
-        r = r * (1.0f - A.ar_strength) + cl * A.ar_strength;
-      } else {
-        r = fminf(fmaxf(r, 0.f), 1.f);
+      for (int c = 0; c < C; ++c) {
+        float r = res[c];
+        if constexpr (AR) {
+          const float hiv = __fdividef(hi2[c], hi[c]) - 0.1f;
+          const float lov = 1.1f - __fdividef(lo2[c], lo[c]);
+          const float cl = fminf(fmaxf(r, lov), hiv);
+          r = r * (1.0f - A.ar_strength) + cl * A.ar_strength;
+        } else {
+          r = fminf(fmaxf(r, 0.f), 1.f);
+        }
+        __stcs(A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r);
       }
-      __stcs(A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r);
     }
   }
 }
 
-template <int R, int C, int KEYMODE, bool AR>
-int launch_zoom(const ZoomArgs& a0, int device, cudaStream_t stream) {
+template <int R, int C, int KEYMODE, bool AR, bool LUTH>
+int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   ZoomArgs a = a0;
   a.tiles_x = (a.ow + kTOW - 1) / kTOW;
   a.tiles_y = (a.oh + kTOH - 1) / kTOH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_zoom_kernel<R, C, KEYMODE, AR>;
+  auto kern = ravu_zoom_kernel<R, C, KEYMODE, AR, LUTH>;
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, 0));
   if (per_sm < 1) per_sm = 1;
@@ -222,6 +261,12 @@ int launch_zoom(const ZoomArgs& a0, int device, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;
+}
+
+template <int R, int C, int KEYMODE, bool AR>
+int launch_zoom(const ZoomArgs& a, int device, cudaStream_t stream, bool half_lut) {
+  if (half_lut) return launch_zoom_impl<R, C, KEYMODE, AR, true>(a, device, stream);
+  return launch_zoom_impl<R, C, KEYMODE, AR, false>(a, device, stream);
 }
 
 }  // namespace
@@ -252,8 +297,10 @@ extern "C" int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   ZoomArgs a{};
   a.in = in; a.out = out; a.bucket = bucket_out;
-  a.lut = reinterpret_cast<const float4*>(lut->lut);
-  a.lut_ar = lut_ar ? reinterpret_cast<const float4*>(lut_ar->lut) : nullptr;
+  // binary16 texels are exact whenever the LUT was created with round_to_fp16 (the rgba16f policy)
+  const bool half_lut = lut->lut_half && (!lut_ar || lut_ar->lut_half);
+  a.lut = half_lut ? lut->lut_half : static_cast<const void*>(lut->lut);
+  a.lut_ar = lut_ar ? (half_lut ? lut_ar->lut_half : static_cast<const void*>(lut_ar->lut)) : nullptr;
   a.n = n; a.h = h; a.w = w; a.oh = out_h; a.ow = out_w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
   a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;
@@ -263,18 +310,18 @@ extern "C" int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights
   const int dev = lut->device;
   const int ar = lut_ar ? 1 : 0;
   switch ((radius * 3 + key_mode) * 2 + ar) {
-    case 12: return launch_zoom<2, 1, 0, false>(a, dev, st);
-    case 13: return launch_zoom<2, 1, 0, true>(a, dev, st);
-    case 14: return launch_zoom<2, 3, 1, false>(a, dev, st);
-    case 15: return launch_zoom<2, 3, 1, true>(a, dev, st);
-    case 16: return launch_zoom<2, 3, 2, false>(a, dev, st);
-    case 17: return launch_zoom<2, 3, 2, true>(a, dev, st);
-    case 18: return launch_zoom<3, 1, 0, false>(a, dev, st);
-    case 19: return launch_zoom<3, 1, 0, true>(a, dev, st);
-    case 20: return launch_zoom<3, 3, 1, false>(a, dev, st);
-    case 21: return launch_zoom<3, 3, 1, true>(a, dev, st);
-    case 22: return launch_zoom<3, 3, 2, false>(a, dev, st);
-    case 23: return launch_zoom<3, 3, 2, true>(a, dev, st);
+    case 12: return launch_zoom<2, 1, 0, false>(a, dev, st, half_lut);
+    case 13: return launch_zoom<2, 1, 0, true>(a, dev, st, half_lut);
+    case 14: return launch_zoom<2, 3, 1, false>(a, dev, st, half_lut);
+    case 15: return launch_zoom<2, 3, 1, true>(a, dev, st, half_lut);
+    case 16: return launch_zoom<2, 3, 2, false>(a, dev, st, half_lut);
+    case 17: return launch_zoom<2, 3, 2, true>(a, dev, st, half_lut);
+    case 18: return launch_zoom<3, 1, 0, false>(a, dev, st, half_lut);
+    case 19: return launch_zoom<3, 1, 0, true>(a, dev, st, half_lut);
+    case 20: return launch_zoom<3, 3, 1, false>(a, dev, st, half_lut);
+    case 21: return launch_zoom<3, 3, 1, true>(a, dev, st, half_lut);
+    case 22: return launch_zoom<3, 3, 2, false>(a, dev, st, half_lut);
+    case 23: return launch_zoom<3, 3, 2, true>(a, dev, st, half_lut);
   }
   return MPVP_E_INVALID;
 }

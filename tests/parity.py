@@ -36,6 +36,12 @@ def boundary_distance(key, v):
     return d_angle, d_str, d_coh
 
 
+def on_edge_mask(key, v):
+    """Key evaluations that sit on a bucket edge to within a few ulps."""
+    d_angle, d_str, d_coh = boundary_distance(key, v)
+    return (d_angle < 1e-4) | (d_str < 1e-5) | (d_coh < 1e-5)
+
+
 def check_buckets(got_rows, key, v, what=""):
     """got_rows, key.row: same shape.  Returns the agreement mask.
 
