@@ -10,13 +10,14 @@
 //   B  [K/8][2*nns][8 halfs] binary16, resident in shared memory for the whole kernel, fetched once per CTA
 //      with one TMA bulk copy (cp.async.bulk -> mbarrier); rows interleave (W1_n * log2e, W2_n);
 //      the biases ride along as one extra K step (A columns 1,1,1,0..; B rows bias hi/mid/lo);
-//   D  fp32 in tensor memory: 128 lanes (pixels) x 128-column chunks (64 neurons);
+//   D  fp32 in tensor memory: 128 lanes (pixels) x 128-column chunks (64 neurons); the MMA of chunk c+1 is
+//      issued as soon as the last columns of chunk c have been loaded into registers;
 //   epilogue: tcgen05.ld 32x32b (thread == pixel == TMEM lane, next load in flight while the current
 //      one is consumed) -> ex2 (MUFU), reciprocal (MUFU or two Newton steps on the FMA pipe), running sums.
 //
 // Four independent warpgroups per CTA (128 threads each) walk 32x4-pixel tiles; each owns a quarter of
-// TMEM (128 columns) and issues its own tcgen05.mma from one elected thread, so one group's MMA latency
-// and A-build hide under the other groups' MUFU/FMA-bound epilogues.
+// TMEM (128 columns) and issues its own tcgen05.mma from one elected thread; the source window of the
+// next tile is staged with cp.async while the current tile's epilogue runs.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   constexpr int KX = K + 16;                // + one MMA K-step carrying the biases
   constexpr int KC = K / 8;                 // 16-byte K chunks written per tile
   constexpr int N = 2 * NNS;                // accumulator columns per pixel
-  constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk
+  constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk (64 neurons)
   constexpr int NCH = N / CN;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
@@ -163,8 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   unsigned char* s_b = smem;                               // B operand
   unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
   float* s_stage = reinterpret_cast<float*>(s_a + kWG * kABytes);  // [kWG][STG]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG] + 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + kWG + 1);
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] + 1
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 2 * kWG + 1);
 
   const int tid = threadIdx.x;
   const int wg = tid >> 7;       // warpgroup
@@ -172,9 +173,9 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const int warp = tid >> 5;
   const int tx = lt & 31, ty = lt >> 5;
 
-  const uint32_t mbar_b = smem_u32(s_mbar + kWG);
+  const uint32_t mbar_b = smem_u32(s_mbar + 2 * kWG);
   if (tid == 0) {
-    for (int i = 0; i < kWG; ++i) mbar_init(smem_u32(s_mbar + i), 1);
+    for (int i = 0; i < 2 * kWG; ++i) mbar_init(smem_u32(s_mbar + i), 1);
     mbar_init(mbar_b, 1);
     fence_mbar_init();
   }
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   float* my_stage = s_stage + wg * STG;
   const uint32_t a_addr = smem_u32(my_a), b_addr = smem_u32(s_b);
   const uint32_t idesc = make_idesc(CN);
-  const uint32_t my_mbar = smem_u32(s_mbar + wg);
+  const uint32_t my_mbar = smem_u32(s_mbar + 2 * wg);
   const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
   const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
@@ -220,21 +221,36 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     umma_commit(my_mbar);
   };
 
-  for (long long tile = (long long)blockIdx.x * kWG + wg; tile < A.total_tiles; tile += (long long)gridDim.x * kWG) {
+  // asynchronous staging of a tile's source rectangle (clamp-to-edge): cp.async, no registers held, so the
+  // loads of tile t+1 fly under the epilogue of tile t
+  auto prefetch_tile = [&](long long tile) {
+    if (tile >= A.total_tiles) return;
     const int tix = (int)(tile % A.tiles_x);
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int x0 = tix * kTileW, y0 = tiy * kTileH;
     const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
-
-    // ---- stage the source rectangle (clamp-to-edge) -------------------------------------------
-    wg_barrier(wg);  // previous tile's window reads are done
     for (int i = lt; i < SW * SH; i += 128) {
       const int sy = i / SW, sx = i - sy * SW;
       const int gx = clampi(x0 + sx - OX, 0, A.w - 1), gy = clampi(y0 + sy - OY, 0, A.h - 1);
-      my_stage[i] = __ldg(src + (int64_t)gy * A.in_sy + gx);
+      const uint32_t dst = smem_u32(my_stage + i);
+      const float* g = src + (int64_t)gy * A.in_sy + gx;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
     }
-    wg_barrier(wg);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const long long tile_step = (long long)gridDim.x * kWG;
+  prefetch_tile((long long)blockIdx.x * kWG + wg);
+
+  for (long long tile = (long long)blockIdx.x * kWG + wg; tile < A.total_tiles; tile += tile_step) {
+    const int tix = (int)(tile % A.tiles_x);
+    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
+    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const int x0 = tix * kTileW, y0 = tiy * kTileH;
+
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    wg_barrier(wg);  // the staged window of this tile is complete and visible
 
     // ---- im2col + normalisation -> A operand ----------------------------------------------------
     float mstd0, mstd1, orig;
@@ -270,11 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     }
     fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor core (async proxy)
     tc_fence_before();     // orders the previous tile's tcgen05.ld before the new MMAs
-    wg_barrier(wg);
+    wg_barrier(wg);        // A complete; nobody reads the staging buffer any more
     if (lt == 0) {
       tc_fence_after();
       issue_chunk(0);
     }
+    prefetch_tile(tile + tile_step);
 
     // ---- epilogue -----------------------------------------------------------------------------
     float wsum = 0.f, vsum = 0.f;
@@ -291,7 +308,18 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
         uint32_t (&cur)[32] = (i & 1) ? vb : va;
         uint32_t (&nxt)[32] = (i & 1) ? va : vb;
         tmem_ld_wait();
-        if (i + 1 < CN / 32) tmem_ld32_issue(d_lane + (i + 1) * 32, nxt);
+        if (i + 1 < CN / 32) {
+          tmem_ld32_issue(d_lane + (i + 1) * 32, nxt);
+        } else if (c + 1 < NCH) {
+          // the last columns of this chunk are in registers: the accumulator is free, so the MMA of the
+          // next chunk is issued now and runs under the arithmetic of this last block
+          tc_fence_before();
+          wg_barrier(wg);
+          if (lt == 0) {
+            tc_fence_after();
+            issue_chunk(c + 1);
+          }
+        }
         // registers 0..15: softmax logits of 16 neurons, 16..31: their elliott inputs
         if constexpr (EPI == 2) {
           // packed f32x2: two neurons per instruction on the FMA pipe
@@ -323,14 +351,6 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
             wsum += s1;
             vsum = fmaf(s1 * t, r, vsum);
           }
-        }
-      }
-      if (c + 1 < NCH) {  // the TMEM columns are free again: next chunk of neurons
-        tc_fence_before();
-        wg_barrier(wg);
-        if (lt == 0) {
-          tc_fence_after();
-          issue_chunk(c + 1);
         }
       }
     }
@@ -376,7 +396,7 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
   constexpr int STG = (SW * SH + 3) & ~3;
-  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (kWG + 1) + 16;
+  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (2 * kWG + 1) + 16;
   // one CTA per SM: the kernel allocates all 512 TMEM columns
   if (smem < 120 * 1024) smem = 120 * 1024;
   NnTcArgs a = a0;
