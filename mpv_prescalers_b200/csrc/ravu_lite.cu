@@ -7,12 +7,18 @@
 // Design (B200): persistent CTAs (grid = SMs x resident CTAs) walk a (frame, tile) work list.  The
 // whole LUT lives in shared memory for the lifetime of the CTA (r3: 288 x 13 float4 = 58.5 KB;
 // values are exactly the fp16-rounded texels the reference's rgba16f texture holds).  A CTA stages
-// one input tile + halo in shared memory (clamp-to-edge applied while staging), then every thread
+// one input tile + halo in shared memory -- by TMA (cp.async.bulk.tensor.3d into a double buffer, the
+// next tile in flight while the current one is computed; out-of-image halo texels, which TMA zero-fills,
+// are patched in shared memory to the reference's clamp-to-edge) when the plane is 16-byte aligned, else
+// by plain clamped loads -- then every thread
 // walks a vertical strip of P pixels keeping the (P + 2o) x n luma window in registers, so that
 // gradients, and the (0.1+l)^32 / (1.1-l)^32 anti-ringing powers are computed once per source
 // pixel and reused by every output pixel that taps them.  All 4 (or 9) sub-pixel phases are
 // written interleaved with 8-byte coalesced streaming stores.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -57,9 +63,38 @@ __device__ __forceinline__ float rgb_luma709(float r, float g, float b) {
 }
 
 // C = colour channels (1 or 3; 3 only for SCALE == 3), KEYMODE: 0 luma, 1 yuv (key = channel 0), 2 rgb
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait_parity(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
+// true for exactly one lane of a fully converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA>
 __global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : 2))
-ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
+ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
   static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
   using Gm = LiteGeom<R>;
   constexpr int N = Gm::N, O = Gm::O, G = Gm::G, TAPS = Gm::TAPS, HALF = Gm::HALF;
@@ -67,30 +102,87 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
   constexpr int ROWS = (SCALE == 2) ? 288 : 216;
   constexpr int TR = kThreads / kTW;          // thread rows
   constexpr int TH = TR * P * STRIPS;         // tile height
-  constexpr int SW = kTW + 2 * O;             // staged tile width
+  // TMA needs the box to START on a 16-byte boundary and its rows to be multiples of 16 bytes (an x origin of
+  // x0 - O is rejected as an illegal instruction, tools/tma_min.cu): the TMA box starts 4 texels left of the tile
+  constexpr int XO = TMA ? 4 : O;             // staged columns left of the tile
+  constexpr int SW = TMA ? (kTW + 8) : ((kTW + 2 * O + 3) & ~3);  // staged row pitch
   constexpr int SH = TH + 2 * O;
   constexpr int PLANE = SW * SH;              // plane 0 = key plane, planes 1..3 = colours (C == 3)
+  constexpr int TBUF = ((PLANE * 4 + 127) / 128) * 32;  // floats per TMA buffer (128-byte aligned)
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
-  float* s_tile = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LW);
+  float* s_tiles = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LW);
+  __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
+  if constexpr (TMA) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_mbar[0])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_mbar[1])) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[i] = A.lut[i];
+  __syncthreads();
 
   const int tx = tid % kTW, tr = tid / kTW;
 
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+  // one thread asks the TMA engine for the (SW x SH) box of `tile` (origin may be negative: OOB -> 0)
+  const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);  // address of the __grid_constant__ parameter itself
+  auto tma_issue = [&, tmap_ptr](long long tile, int buf) {
+    const int tix = (int)(tile % A.tiles_x);
+    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
+    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const uint32_t bar = smem_addr(&s_mbar[buf]);
+    const uint32_t dst = smem_addr(s_tiles + buf * TBUF);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PLANE * 4) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap_ptr), "r"(tix * kTW - XO), "r"(tiy * TH - O), "r"(f), "r"(bar)
+        : "memory");
+  };
+  if constexpr (TMA) {
+    if (tid < 32 && blockIdx.x < A.total_tiles) {
+      if (elect_one()) tma_issue(blockIdx.x, 0);
+    }
+  }
+
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
     const int tix = (int)(tile % A.tiles_x);
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int x0 = tix * kTW, y0 = tiy * TH;
     const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+    float* __restrict__ s_tile = s_tiles + (TMA ? (it & 1) * TBUF : 0);
 
-    __syncthreads();  // previous tile fully consumed (also orders the LUT fill on the first trip)
+    if constexpr (TMA) {
+      // the other buffer was released by the barrier that ended the previous iteration
+      if (tid < 32 && tile + gridDim.x < A.total_tiles) {
+        if (elect_one()) tma_issue(tile + gridDim.x, (it + 1) & 1);
+      }
+      mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
+      const bool edge = x0 - XO < 0 || y0 - O < 0 || x0 - XO + SW > A.w || y0 - O + SH > A.h;
+      if (edge) {  // CTA-uniform: replicate the border (clamp-to-edge) over the zero-filled texels
+        for (int i = tid; i < PLANE; i += kThreads) {
+          const int sy = i / SW, sx = i - sy * SW;
+          const int gx = x0 - XO + sx, gy = y0 - O + sy;
+          if (gy >= 0 && gy < A.h && (gx < 0 || gx >= A.w)) s_tile[i] = s_tile[sy * SW + clampi(gx, 0, A.w - 1) - (x0 - XO)];
+        }
+        __syncthreads();
+        for (int i = tid; i < PLANE; i += kThreads) {
+          const int sy = i / SW, sx = i - sy * SW;
+          const int gy = y0 - O + sy;
+          if (gy < 0 || gy >= A.h) s_tile[i] = s_tile[(clampi(gy, 0, A.h - 1) - (y0 - O)) * SW + sx];
+        }
+        __syncthreads();
+      }
+    } else {
+    __syncthreads();  // previous tile fully consumed
     for (int i = tid; i < SW * SH; i += kThreads) {
       const int sy = i / SW, sx = i - sy * SW;
-      const int gx = clampi(x0 + sx - O, 0, A.w - 1);
+      const int gx = clampi(x0 + sx - XO, 0, A.w - 1);
       const int gy = clampi(y0 + sy - O, 0, A.h - 1);
       const int64_t off = (int64_t)gy * A.in_sy + gx;
       if constexpr (C == 1) {
@@ -104,6 +196,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
       }
     }
     __syncthreads();
+    }
 
     const int x = x0 + tx;
 #pragma unroll 1
@@ -117,7 +210,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
 #pragma unroll
       for (int yy = 0; yy < P + 2 * O; ++yy)
 #pragma unroll
-        for (int xx = 0; xx < N; ++xx) l[yy][xx] = s_tile[(ly0 + yy) * SW + tx + xx];
+        for (int xx = 0; xx < N; ++xx) l[yy][xx] = s_tile[(ly0 + yy) * SW + tx + xx + (XO - O)];
 
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -200,7 +293,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
             // colour sample of channel c at window tap (i, j)
             auto Cn = [&](int i, int j) -> float {
               if constexpr (C == 1) return l[p + j][i];
-              else return s_tile[(1 + c) * PLANE + (ly0 + p + j) * SW + tx + i];
+              else return s_tile[(1 + c) * PLANE + (ly0 + p + j) * SW + tx + i + (XO - O)];
             };
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
@@ -228,7 +321,51 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A) {
         }
       }
     }
+    if constexpr (TMA) {
+      // this buffer may be refilled by the TMA (async proxy) issued at the top of the next iteration
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
   }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// MPVP_TMA=0 forces the plain-load staging path (A/B switch)
+bool tma_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("MPVP_TMA");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+// 3-D tensor map {w, h, n} over the input planes with a (box_w x box_h x 1) box; false if the layout does not
+// meet TMA's 16-byte rules (then the kernel stages with plain loads)
+bool make_plane_tmap(CUtensorMap* tm, const float* base, int w, int h, int n, int64_t sy, int64_t sn, int box_w, int box_h) {
+  if (!tma_enabled() || !encode_tiled()) return false;
+  if (n == 1) sn = (int64_t)h * sy;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (sy * 4) % 16 || (sn * 4) % 16 || sy < w || box_w > 256 || box_h > 256) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[2] = {(cuuint64_t)sy * 4, (cuuint64_t)sn * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
@@ -237,13 +374,22 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   constexpr int LW = (SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1);
   constexpr int ROWS = (SCALE == 2) ? 288 : 216;
   constexpr int TH = (kThreads / kTW) * P * STRIPS;
-  constexpr int SW = kTW + 2 * Gm::O, SH = TH + 2 * Gm::O;
-  const size_t smem = sizeof(float4) * ROWS * LW + sizeof(float) * SW * SH * (C == 1 ? 1 : 4);
+  constexpr int SW = (kTW + 2 * Gm::O + 3) & ~3, SH = TH + 2 * Gm::O;   // plain-load staging
+  constexpr int SWT = kTW + 8;                                           // TMA box width (starts at x0 - 4)
+  constexpr int TBUF = ((SWT * SH * 4 + 127) / 128) * 32;
   LiteArgs a = a0;
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + TH - 1) / TH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY>;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  bool use_tma = false;
+  if constexpr (C == 1) use_tma = make_plane_tmap(&tmap, a.in, a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
+  const size_t smem = sizeof(float4) * ROWS * LW + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4));
+  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false>;
+  if constexpr (C == 1) {
+    if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true>;
+  }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -254,7 +400,7 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   long long grid = (long long)sm_count(device) * per_sm;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (grid < 1) return MPVP_OK;
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, tmap);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;
