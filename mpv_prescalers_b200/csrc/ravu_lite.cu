@@ -467,7 +467,7 @@ extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_par
     case 4: return launch_lite<2, false, 2, 4, 2>(a, lut->device, st);
     case 5: return launch_lite<2, true, 2, 4, 2>(a, lut->device, st);
     case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
-    case 7: return launch_lite<3, true, 2, 4, 2>(a, lut->device, st);
+    case 7: return launch_lite<3, true, 2, 2, 4>(a, lut->device, st);  // P=2: the strip body must fit the 32 KB I-cache
     case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
     case 9: return launch_lite<4, true, 2, 2, 4>(a, lut->device, st);
   }

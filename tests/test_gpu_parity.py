@@ -338,3 +338,48 @@ def test_c_abi_error_convention():
     assert rc < 0 and b"LUT is" in lib.mpvp_last_error()
     rc = lib.mpvp_ravu_lite_launch(None, ctypes.byref(W.key), 3, 0, 0.0, x.data_ptr(), o.data_ptr(), 1, 8, 8, 64, 8, 256, 16, None, None)
     assert rc < 0
+
+
+def _available_hooks():
+    import glob
+    import os
+
+    from mpv_prescalers_b200.hookfile import find_hook
+
+    try:
+        root = os.path.dirname(find_hook("ravu-lite-ar-r3.hook"))
+    except Exception:
+        return []
+    files = sorted(glob.glob(os.path.join(root, "*.hook")) + glob.glob(os.path.join(root, "*", "*.hook")))
+    return [os.path.relpath(f, root) for f in files]
+
+
+@pytest.mark.parametrize("rel", _available_hooks())
+def test_every_available_hook_runs_and_flavours_agree(rel):
+    """Every shipped file that is present (99 under /root/reference, the staged subset on the GPU box) goes
+    through prescale(); gather/ and compute/ flavours are aliases of the same math and must reproduce their
+    root twin bit for bit."""
+    import os
+
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.hookfile import find_hook
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(rel))
+    v = hk.variant
+    x = torch.from_numpy(batch(1, v.channels, 40, 56, config=51)).cuda()
+    osz = (93, 131) if v.family == "ravu-zoom" else None
+    out = prescale(x, hk, output_size=osz)
+    torch.cuda.synchronize()
+    assert out.applied and torch.isfinite(out).all()
+    exp = {"ravu-lite": (80, 112), "ravu": (80, 112), "ravu-3x": (120, 168), "ravu-zoom": (93, 131), "nnedi3": (80, 112)}[v.family]
+    assert tuple(out.shape[-2:]) == exp
+    if "/" in rel:
+        twin = os.path.basename(rel)
+        try:
+            twin_path = find_hook(twin)
+        except Exception:
+            return
+        ref = prescale(x, HookFile.parse(twin_path), output_size=osz)
+        assert torch.equal(out, ref), f"{rel} differs from its root twin {twin}"

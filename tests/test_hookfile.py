@@ -158,3 +158,26 @@ def test_missing_zoom_ar_r3_is_named():
 
     with pytest.raises(HookError, match="MISSING_LARGE_BLOBS"):
         find_hook("ravu-zoom-ar-r3.hook")
+
+
+@pytest.mark.skipif(not ALL, reason="reference snapshot not mounted")
+def test_flavours_carry_identical_payloads_and_constants():
+    """root / gather / compute files of one variant ship the same LUT bytes and the same key constants."""
+    by_name = {}
+    for f in ALL:
+        by_name.setdefault(os.path.basename(f), []).append(f)
+    checked = 0
+    for name, files in by_name.items():
+        if len(files) < 2:
+            continue
+        vs = [HookFile.parse(f).variant for f in files]
+        base = vs[0]
+        for v in vs[1:]:
+            assert (v.family, v.radius, v.ar, v.plane, v.nns, v.win) == (base.family, base.radius, base.ar, base.plane, base.nns, base.win)
+            if base.lut is not None:
+                assert v.lut.sha16 == base.lut.sha16
+                assert np.array_equal(v.gauss, base.gauss) and v.strength_thr == base.strength_thr
+            if base.nn_y is not None:
+                assert np.array_equal(v.nn_y.w1, base.nn_y.w1) and np.array_equal(v.nn_x.w2, base.nn_x.w2)
+            checked += 1
+    assert checked >= 40
