@@ -42,11 +42,12 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4
                                          float (&res)[C]) {
   constexpr int N = 2 * R, TAPS = N * N, G = (R == 4) ? 6 : 4;
   constexpr int LW = (TAPS / 2 + 3) / 4;
+  constexpr int LWP = LW | 1;  // odd float4 pitch in shared memory: rows spread over all banks (r4: 8 -> 9)
   float ks[TAPS];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) ks[t] = KS(t);
   const int row = ravu_key2<STENCIL_RAVU, N, G, 8, true>(kp, [&](int i, int j) { return ks[i * N + j]; });
-  const float4* __restrict__ wrow = s_lut + row * LW;
+  const float4* __restrict__ wrow = s_lut + row * LWP;
 #pragma unroll
   for (int c = 0; c < C; ++c) res[c] = 0.f;
 #pragma unroll
@@ -76,6 +77,7 @@ template <int R, int C, int KEYMODE, int NT>
 __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
   constexpr int N = 2 * R, TAPS = N * N;
   constexpr int LW = (TAPS / 2 + 3) / 4;
+  constexpr int LWP = LW | 1;
   constexpr int HH = 2 * R - 1;              // HOOKED halo
   constexpr int HW_ = kTW + 2 * HH, HHt = kTH + 2 * HH;   // staged HOOKED tile
   constexpr int IW = kTW + 2 * R - 1, IH = kTH + 2 * R - 1;  // int11 tile: x' in [x0-R, x0+TW+R-2]
@@ -84,11 +86,11 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
-  float* s_h = reinterpret_cast<float*>(smem_raw + sizeof(float4) * 648 * LW);  // [NP][HHt][HW_]
+  float* s_h = reinterpret_cast<float*>(smem_raw + sizeof(float4) * 648 * LWP);  // [NP][HHt][HW_]
   float* s_i = s_h + NP * HHt * HW_;                                             // [NP][IH][IW]
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < 648 * LW; i += NT) s_lut[i] = A.lut[i];
+  for (int i = tid; i < 648 * LW; i += NT) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
 
   for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
     const int tix = (int)(tile % A.tiles_x);
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
 
 template <int R, int C, int KEYMODE, int NT>
 int launch_ravu(const RavuArgs& a0, int device, cudaStream_t stream) {
-  constexpr int N = 2 * R, TAPS = N * N, LW = (TAPS / 2 + 3) / 4, HH = 2 * R - 1;
+  constexpr int N = 2 * R, TAPS = N * N, LW = ((TAPS / 2 + 3) / 4) | 1, HH = 2 * R - 1;  // LW: padded pitch
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
   const size_t smem = sizeof(float4) * 648 * LW +
                       sizeof(float) * NP * ((kTW + 2 * HH) * (kTH + 2 * HH) + (kTW + 2 * R - 1) * (kTH + 2 * R - 1));

@@ -99,6 +99,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
   using Gm = LiteGeom<R>;
   constexpr int N = Gm::N, O = Gm::O, G = Gm::G, TAPS = Gm::TAPS, HALF = Gm::HALF;
   constexpr int LW = (SCALE == 2) ? (TAPS + 1) / 2 : (TAPS + 1);
+  constexpr int LWP = LW | 1;  // odd float4 pitch in shared memory (3x: 10/26/50 -> 11/27/51): no row-to-row bank aliasing
   constexpr int ROWS = (SCALE == 2) ? 288 : 216;
   constexpr int TR = kThreads / kTW;          // thread rows
   constexpr int TH = TR * P * STRIPS;         // tile height
@@ -112,7 +113,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
-  float* s_tiles = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LW);
+  float* s_tiles = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LWP);
   __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
@@ -123,7 +124,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[i] = A.lut[i];
+  for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
   __syncthreads();
 
   const int tx = tid % kTW, tr = tid / kTW;
@@ -221,7 +222,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
         auto Wn = [&](int i, int j) { return l[p + j][i]; };
         const int row = ravu_key2<STENCIL_LITE, N, G, (SCALE == 2 ? 3 : 2), FASTKEY>(A.key, Wn);
         if (A.bucket && live) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
-        const float4* __restrict__ wrow = s_lut + row * LW;
+        const float4* __restrict__ wrow = s_lut + row * LWP;
 
         if constexpr (SCALE == 2) {
           float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
@@ -371,7 +372,7 @@ bool make_plane_tmap(CUtensorMap* tm, const float* base, int w, int h, int n, in
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
 int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   using Gm = LiteGeom<R>;
-  constexpr int LW = (SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1);
+  constexpr int LW = ((SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1)) | 1;  // padded pitch
   constexpr int ROWS = (SCALE == 2) ? 288 : 216;
   constexpr int TH = (kThreads / kTW) * P * STRIPS;
   constexpr int SW = (kTW + 2 * Gm::O + 3) & ~3, SH = TH + 2 * Gm::O;   // plain-load staging
