@@ -16,6 +16,7 @@
 // pixel and reused by every output pixel that taps them.  All 4 (or 9) sub-pixel phases are
 // written interleaved with 8-byte coalesced streaming stores.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,7 @@ struct LiteArgs {
   const float* __restrict__ in;
   float* __restrict__ out;
   const float4* __restrict__ lut;  // [rows][LW]
+  const uint2* __restrict__ lut_half;  // same texels as 4 x binary16 (present when the LUT was rounded to fp16)
   int32_t* __restrict__ bucket;
   int n, h, w;
   int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
@@ -91,7 +93,10 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA>
+// LH: LUT kept in shared memory as 4 x binary16 per texel (exact: the texels ARE binary16 values, App. D.1).  A warp's
+// 32 lanes gather 32 different LUT rows, so the gather is bank-conflict bound: 8-byte texels need half the
+// shared-memory wavefronts of 16-byte ones (68 vs 133 per 13-texel row on the config-2 planes).
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH>
 __global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : 2))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
@@ -110,10 +115,17 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
   constexpr int SH = TH + 2 * O;
   constexpr int PLANE = SW * SH;              // plane 0 = key plane, planes 1..3 = colours (C == 3)
   constexpr int TBUF = ((PLANE * 4 + 127) / 128) * 32;  // floats per TMA buffer (128-byte aligned)
+  // anti-ringing: ((0.1+l)^32, (1.1-l)^32, (0.1+l)^33, (1.1-l)^33) of every source pixel the tile's diamonds tap,
+  // computed ONCE per source pixel into shared memory (the shader recomputes them per output pixel and tap)
+  constexpr int AO = O < 2 ? O : 2;           // diamond reach dx^2 + dy^2 <= 4
+  constexpr int PW = kTW + 2 * AO, PH = TH + 2 * AO;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
-  float* s_tiles = reinterpret_cast<float*>(smem_raw + sizeof(float4) * ROWS * LWP);
+  uint2* s_luth = reinterpret_cast<uint2*>(smem_raw);
+  constexpr int kLutBytes = ((int)(LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LWP + 127) & ~127;
+  float* s_tiles = reinterpret_cast<float*>(smem_raw + kLutBytes);
+  float4* s_pow = reinterpret_cast<float4*>(s_tiles + (TMA ? 2 * TBUF : PLANE * (C == 1 ? 1 : 4)));
   __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
@@ -124,7 +136,11 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
+  if constexpr (LH) {
+    for (int i = tid; i < ROWS * LW; i += kThreads) s_luth[(i / LW) * LWP + (i % LW)] = A.lut_half[i];
+  } else {
+    for (int i = tid; i < ROWS * LW; i += kThreads) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
+  }
   __syncthreads();
 
   const int tx = tid % kTW, tr = tid / kTW;
@@ -199,6 +215,17 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
     __syncthreads();
     }
 
+    if constexpr (AR) {
+      for (int i = tid; i < PW * PH; i += kThreads) {
+        const int sy = i / PW, sx = i - sy * PW;
+        const float lv = s_tile[(sy + O - AO) * SW + sx + (XO - AO)];
+        const float c = 0.1f + lv, dd = 1.1f - lv;
+        const float pc = pow32(c), pd = pow32(dd);
+        s_pow[i] = make_float4(pc, pd, pc * c, pd * dd);
+      }
+      __syncthreads();
+    }
+
     const int x = x0 + tx;
 #pragma unroll 1
     for (int s = 0; s < STRIPS; ++s) {
@@ -222,46 +249,56 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
         auto Wn = [&](int i, int j) { return l[p + j][i]; };
         const int row = ravu_key2<STENCIL_LITE, N, G, (SCALE == 2 ? 3 : 2), FASTKEY>(A.key, Wn);
         if (A.bucket && live) A.bucket[((int64_t)f * A.h + y) * A.w + x] = row;
-        const float4* __restrict__ wrow = s_lut + row * LWP;
+        // texel t of this pixel's LUT row
+        auto texel = [&](int t) -> float4 {
+          if constexpr (LH) {
+            const uint2 u = s_luth[row * LWP + t];
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+          } else {
+            return s_lut[row * LWP + t];
+          }
+        };
 
         if constexpr (SCALE == 2) {
           float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-          float hi[4], lo[4], hi2[4], lo2[4];
+          // (hi, lo)[c] and (hi2, lo2)[c] as packed f32x2 accumulators: one FFMA2 updates both
+          float2 hl[4], hl2[4];
           if constexpr (AR) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
+            for (int c = 0; c < 4; ++c) hl[c] = hl2[c] = make_float2(0.f, 0.f);
           }
+          [[maybe_unused]] const float4* __restrict__ prow = s_pow + (ly0 + p + AO) * PW + tx + AO;
 #pragma unroll
           for (int t = 0; t <= HALF; ++t) {
-            const float4 w = wrow[t];
+            const float4 w = texel(t);
             const float la = Wn(t / N, t % N);
             r0 = fmaf(la, w.x, r0); r1 = fmaf(la, w.y, r1); r2 = fmaf(la, w.z, r2); r3 = fmaf(la, w.w, r3);
-            float lb = 0.f;
             if (t < HALF) {
-              lb = Wn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
+              const float lb = Wn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
               r0 = fmaf(lb, w.w, r0); r1 = fmaf(lb, w.z, r1); r2 = fmaf(lb, w.y, r2); r3 = fmaf(lb, w.x, r3);
             }
             if constexpr (AR) {
               if (ar_tap<R>(t)) {
                 const float g0 = fmaxf(w.x, 0.f), g1 = fmaxf(w.y, 0.f), g2 = fmaxf(w.z, 0.f), g3 = fmaxf(w.w, 0.f);
+                const float2 G[4] = {make_float2(g0, g0), make_float2(g1, g1), make_float2(g2, g2), make_float2(g3, g3)};
                 {
-                  {
-                    const float c = 0.1f + la, dd = 1.1f - la;
-                    const float pc = pow32(c), pd = pow32(dd);
-                    const float pc1 = pc * c, pd1 = pd * dd;
-                    hi[0] = fmaf(pc, g0, hi[0]); hi[1] = fmaf(pc, g1, hi[1]); hi[2] = fmaf(pc, g2, hi[2]); hi[3] = fmaf(pc, g3, hi[3]);
-                    lo[0] = fmaf(pd, g0, lo[0]); lo[1] = fmaf(pd, g1, lo[1]); lo[2] = fmaf(pd, g2, lo[2]); lo[3] = fmaf(pd, g3, lo[3]);
-                    hi2[0] = fmaf(pc1, g0, hi2[0]); hi2[1] = fmaf(pc1, g1, hi2[1]); hi2[2] = fmaf(pc1, g2, hi2[2]); hi2[3] = fmaf(pc1, g3, hi2[3]);
-                    lo2[0] = fmaf(pd1, g0, lo2[0]); lo2[1] = fmaf(pd1, g1, lo2[1]); lo2[2] = fmaf(pd1, g2, lo2[2]); lo2[3] = fmaf(pd1, g3, lo2[3]);
+                  const float4 pa = prow[(t % N - O) * PW + (t / N - O)];
+                  const float2 a1 = make_float2(pa.x, pa.y), a2 = make_float2(pa.z, pa.w);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    hl[c] = __ffma2_rn(a1, G[c], hl[c]);
+                    hl2[c] = __ffma2_rn(a2, G[c], hl2[c]);
                   }
-                  if (t < HALF) {
-                    const float c = 0.1f + lb, dd = 1.1f - lb;
-                    const float pc = pow32(c), pd = pow32(dd);
-                    const float pc1 = pc * c, pd1 = pd * dd;
-                    hi[0] = fmaf(pc, g3, hi[0]); hi[1] = fmaf(pc, g2, hi[1]); hi[2] = fmaf(pc, g1, hi[2]); hi[3] = fmaf(pc, g0, hi[3]);
-                    lo[0] = fmaf(pd, g3, lo[0]); lo[1] = fmaf(pd, g2, lo[1]); lo[2] = fmaf(pd, g1, lo[2]); lo[3] = fmaf(pd, g0, lo[3]);
-                    hi2[0] = fmaf(pc1, g3, hi2[0]); hi2[1] = fmaf(pc1, g2, hi2[1]); hi2[2] = fmaf(pc1, g1, hi2[2]); hi2[3] = fmaf(pc1, g0, hi2[3]);
-                    lo2[0] = fmaf(pd1, g3, lo2[0]); lo2[1] = fmaf(pd1, g2, lo2[1]); lo2[2] = fmaf(pd1, g1, lo2[2]); lo2[3] = fmaf(pd1, g0, lo2[3]);
+                }
+                if (t < HALF) {
+                  const float4 pb = prow[-(t % N - O) * PW - (t / N - O)];
+                  const float2 b1 = make_float2(pb.x, pb.y), b2 = make_float2(pb.z, pb.w);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    hl[c] = __ffma2_rn(b1, G[3 - c], hl[c]);
+                    hl2[c] = __ffma2_rn(b2, G[3 - c], hl2[c]);
                   }
                 }
               }
@@ -272,8 +309,8 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
             const float st = A.ar_strength;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float lov = 1.1f - __fdividef(lo2[c], lo[c]);
-              const float hiv = __fdividef(hi2[c], hi[c]) - 0.1f;
+              const float lov = 1.1f - __fdividef(hl2[c].y, hl[c].y);
+              const float hiv = __fdividef(hl2[c].x, hl[c].x) - 0.1f;
               const float cl = fminf(fmaxf(res[c], lov), hiv);
               res[c] = res[c] * (1.0f - st) + cl * st;
             }
@@ -299,7 +336,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
             for (int t = 0; t <= HALF; ++t) {
-              const float4 w0 = wrow[2 * t], w1 = wrow[2 * t + 1];
+              const float4 w0 = texel(2 * t), w1 = texel(2 * t + 1);
               const float la = Cn(t / N, t % N);
               a0 = fmaf(la, w0.x, a0); a1 = fmaf(la, w0.y, a1); a2 = fmaf(la, w0.z, a2); a3 = fmaf(la, w0.w, a3);
               b0 = fmaf(la, w1.x, b0); b1 = fmaf(la, w1.y, b1); b2 = fmaf(la, w1.z, b2); b3 = fmaf(la, w1.w, b3);
@@ -369,7 +406,7 @@ bool make_plane_tmap(CUtensorMap* tm, const float* base, int w, int h, int n, in
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY>
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool LH>
 int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   using Gm = LiteGeom<R>;
   constexpr int LW = ((SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1)) | 1;  // padded pitch
@@ -386,10 +423,12 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   memset(&tmap, 0, sizeof(tmap));
   bool use_tma = false;
   if constexpr (C == 1) use_tma = make_plane_tmap(&tmap, a.in, a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
-  const size_t smem = sizeof(float4) * ROWS * LW + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4));
-  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false>;
+  constexpr int AO = Gm::O < 2 ? Gm::O : 2;
+  constexpr size_t kPow = AR ? sizeof(float4) * (kTW + 2 * AO) * (TH + 2 * AO) : 0;  // anti-ringing power tile
+  const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LW) + 127) & ~(size_t)127) + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4)) + kPow;
+  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false, LH>;
   if constexpr (C == 1) {
-    if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true>;
+    if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH>;
   }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -417,10 +456,20 @@ bool exact_key() {
   return v;
 }
 
+// MPVP_LUT_SMEM=fp32 keeps 16-byte texels in shared memory (A/B switch)
+bool half_lut_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("MPVP_LUT_SMEM");
+    return !(e && e[0] == 'f' && e[2] == '3');
+  }();
+  return v;
+}
+
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C = 1, int KEYMODE = 0>
 int launch_lite(const LiteArgs& a, int device, cudaStream_t stream) {
-  if (exact_key()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, false>(a, device, stream);
-  return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true>(a, device, stream);
+  if (exact_key()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, false, false>(a, device, stream);
+  if (a.lut_half && half_lut_enabled()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, true>(a, device, stream);
+  return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, false>(a, device, stream);
 }
 
 int check_common(const mpvp_weights* lut, const mpvp_key_params* key, int radius, const void* in, const void* out,
@@ -457,7 +506,7 @@ extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_par
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   LiteArgs a{};
-  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;
   a.in_sc = 0; a.out_sc = 0;
@@ -468,7 +517,7 @@ extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_par
     case 4: return launch_lite<2, false, 2, 4, 2>(a, lut->device, st);
     case 5: return launch_lite<2, true, 2, 4, 2>(a, lut->device, st);
     case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
-    case 7: return launch_lite<3, true, 2, 2, 4>(a, lut->device, st);  // P=2: the strip body must fit the 32 KB I-cache
+    case 7: return launch_lite<3, true, 2, 2, 3>(a, lut->device, st);  // 64x24 tiles: LUT + tiles + power tile, 2 CTAs/SM
     case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
     case 9: return launch_lite<4, true, 2, 2, 4>(a, lut->device, st);
   }
@@ -489,7 +538,7 @@ extern "C" int mpvp_ravu3x_launch(const mpvp_weights* lut, const mpvp_key_params
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   LiteArgs a{};
-  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
   a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;
