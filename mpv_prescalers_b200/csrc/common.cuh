@@ -168,6 +168,30 @@ __device__ __forceinline__ int ravu_key(const mpvp_key_params& kp, WF W) {
   return key_from_abd(kp, a, b, d);
 }
 
+// Packed f32x2 multiply / add with explicit .rn rounding.  CAUTION (ptxas 12.9): a mul.rn.f32x2 feeding an
+// add.rn.f32x2 IS contracted into one FFMA2 (unlike the scalar mul.rn.f32 / add.rn.f32 pair, and regardless of
+// -fmad=false), which the bucket-parity rule forbids: keep the additions of the key sums scalar.
+__device__ __forceinline__ uint64_t pack2(float2 v) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+  return unpack2(d);
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+  return unpack2(d);
+}
+
 // ---- the same key without sqrt / division / atan2 ------------------------------------------------------
 // Up to (L1, L2) the arithmetic is the shader's, op for op.  The three quantisers are then evaluated on
 // quantities that decide identically except within fp32 rounding noise of a bucket edge:
@@ -227,7 +251,10 @@ __device__ __forceinline__ int ravu_key2(const mpvp_key_params& kp, WF W) {
     return ravu_key<FAMILY, N, G>(kp, W);
   } else {
     constexpr int O = (N - G) / 2;
-    float a = 0.0f, b = 0.0f, d = 0.0f;
+    // (gx^2, gy^2) and their Gaussian weighting as packed FMUL2: each lane rounds exactly like the scalar multiply
+    // of the shader, so the sums are bit-identical to the op-for-op form
+    float2 ad = make_float2(0.0f, 0.0f);
+    float b = 0.0f;
 #pragma unroll
     for (int i = O; i < O + G; ++i) {
 #pragma unroll
@@ -235,12 +262,14 @@ __device__ __forceinline__ int ravu_key2(const mpvp_key_params& kp, WF W) {
         const float gx = key_diff<FAMILY, N>(i, [&](int dd) { return W(i + dd, j); });
         const float gy = key_diff<FAMILY, N>(j, [&](int dd) { return W(i, j + dd); });
         const float g = kp.gauss[(i - O) * G + (j - O)];
-        a = __fadd_rn(a, __fmul_rn(__fmul_rn(gx, gx), g));
+        const float2 gxy = make_float2(gx, gy);
+        const float2 t = mul2_rn(mul2_rn(gxy, gxy), make_float2(g, g));
+        ad.x = __fadd_rn(ad.x, t.x);  // scalar adds: see the note at mul2_rn
+        ad.y = __fadd_rn(ad.y, t.y);
         b = __fadd_rn(b, __fmul_rn(__fmul_rn(gx, gy), g));
-        d = __fadd_rn(d, __fmul_rn(__fmul_rn(gy, gy), g));
       }
     }
-    return key_from_abd_fast<NTHR>(kp, a, b, d);
+    return key_from_abd_fast<NTHR>(kp, ad.x, b, ad.y);
   }
 }
 

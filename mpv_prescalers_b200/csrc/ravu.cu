@@ -11,6 +11,10 @@
 // which is done by evaluating int11 at the clamped coordinate.  Phase B computes int10 and int01
 // from the staged HOOKED tile and the int11 tile and writes the interleaved 2x2 block.  int11 never
 // touches HBM.  -yuv / -rgb variants carry three colour planes plus the key plane.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mpvp {
@@ -20,6 +24,7 @@ struct RavuArgs {
   const float* __restrict__ in;
   float* __restrict__ out;
   const float4* __restrict__ lut;  // [648][LW]
+  const uint2* __restrict__ lut_half;  // same texels as 4 x binary16 (null if the LUT was not rounded to fp16)
   int32_t* __restrict__ bucket;    // [n][3][h][w] or null
   int n, h, w;
   int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
@@ -37,8 +42,10 @@ __device__ __forceinline__ float rgb_luma(float r, float g, float b) {
 }
 
 // One key + convolution.  KS(t) = key sample t, CS(c, t) = colour sample of channel c.
-template <int R, int C, class KF, class CF>
-__device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4* __restrict__ s_lut, KF KS, CF CS,
+// LH: the LUT sits in shared memory as 4 x binary16 per texel (exact, the texels are binary16 values): the
+// per-lane row gather is bank-conflict bound and 8-byte texels need half the wavefronts of 16-byte ones.
+template <int R, int C, bool LH, class KF, class CF>
+__device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* __restrict__ s_lut_raw, KF KS, CF CS,
                                          float (&res)[C]) {
   constexpr int N = 2 * R, TAPS = N * N, G = (R == 4) ? 6 : 4;
   constexpr int LW = (TAPS / 2 + 3) / 4;
@@ -47,13 +54,20 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) ks[t] = KS(t);
   const int row = ravu_key2<STENCIL_RAVU, N, G, 8, true>(kp, [&](int i, int j) { return ks[i * N + j]; });
-  const float4* __restrict__ wrow = s_lut + row * LWP;
 #pragma unroll
   for (int c = 0; c < C; ++c) res[c] = 0.f;
 #pragma unroll
   for (int q = 0; q < LW; ++q) {
-    const float4 w4 = wrow[q];
-    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    float wv[4];
+    if constexpr (LH) {
+      const uint2 u = reinterpret_cast<const uint2*>(s_lut_raw)[row * LWP + q];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      wv[0] = a.x; wv[1] = a.y; wv[2] = b.x; wv[3] = b.y;
+    } else {
+      const float4 w4 = reinterpret_cast<const float4*>(s_lut_raw)[row * LWP + q];
+      wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = q * 4 + e;
@@ -73,7 +87,7 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const float4
 }
 
 // KEYMODE: 0 luma (C=1), 1 yuv (key = channel 0), 2 rgb (key = BT.709 luma)
-template <int R, int C, int KEYMODE, int NT>
+template <int R, int C, int KEYMODE, int NT, bool LH>
 __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
   constexpr int N = 2 * R, TAPS = N * N;
   constexpr int LW = (TAPS / 2 + 3) / 4;
@@ -86,11 +100,16 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
-  float* s_h = reinterpret_cast<float*>(smem_raw + sizeof(float4) * 648 * LWP);  // [NP][HHt][HW_]
+  constexpr int kLutBytes = (int)(LH ? sizeof(uint2) : sizeof(float4)) * 648 * LWP;
+  float* s_h = reinterpret_cast<float*>(smem_raw + ((kLutBytes + 15) & ~15));  // [NP][HHt][HW_]
   float* s_i = s_h + NP * HHt * HW_;                                             // [NP][IH][IW]
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < 648 * LW; i += NT) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
+  if constexpr (LH) {
+    for (int i = tid; i < 648 * LW; i += NT) reinterpret_cast<uint2*>(smem_raw)[(i / LW) * LWP + (i % LW)] = A.lut_half[i];
+  } else {
+    for (int i = tid; i < 648 * LW; i += NT) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
+  }
 
   for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
     const int tix = (int)(tile % A.tiles_x);
@@ -128,7 +147,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const float* __restrict__ kb = s_h + KP * HHt * HW_ + by * HW_ + bx;
       const float* __restrict__ cb = s_h + by * HW_ + bx;
       float res[C];
-      const int row = ravu_conv<R, C>(
+      const int row = ravu_conv<R, C, LH>(
           A.key, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
           [&](int c, int t) { return cb[c * HHt * HW_ + (t % N) * HW_ + (t / N)]; }, res);
 #pragma unroll
@@ -158,7 +177,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
           if ((px2 & 1) == 0) return hb[plane * HHt * HW_ + (py2 / 2) * HW_ + (px2 / 2)];
           return ib[plane * IH * IW + ((py2 - 1) / 2) * IW + ((px2 - 1) / 2)];
         };
-        rows[pass] = ravu_conv<R, C>(
+        rows[pass] = ravu_conv<R, C, LH>(
             A.key, s_lut, [&](int t) { return fetch(KP, t); }, [&](int c, int t) { return fetch(c, t); },
             pass == 0 ? r10 : r01);
       }
@@ -177,17 +196,17 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
   }
 }
 
-template <int R, int C, int KEYMODE, int NT>
-int launch_ravu(const RavuArgs& a0, int device, cudaStream_t stream) {
+template <int R, int C, int KEYMODE, int NT, bool LH>
+int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   constexpr int N = 2 * R, TAPS = N * N, LW = ((TAPS / 2 + 3) / 4) | 1, HH = 2 * R - 1;  // LW: padded pitch
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
-  const size_t smem = sizeof(float4) * 648 * LW +
+  const size_t smem = (((LH ? sizeof(uint2) : sizeof(float4)) * 648 * LW + 15) & ~(size_t)15) +
                       sizeof(float) * NP * ((kTW + 2 * HH) * (kTH + 2 * HH) + (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
   RavuArgs a = a0;
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + kTH - 1) / kTH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_kernel<R, C, KEYMODE, NT>;
+  auto kern = ravu_kernel<R, C, KEYMODE, NT, LH>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -202,6 +221,17 @@ int launch_ravu(const RavuArgs& a0, int device, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;
+}
+
+// MPVP_LUT_SMEM=fp32 keeps 16-byte texels in shared memory (A/B switch)
+template <int R, int C, int KEYMODE, int NT>
+int launch_ravu(const RavuArgs& a, int device, cudaStream_t stream) {
+  static const bool half_ok = [] {
+    const char* e = getenv("MPVP_LUT_SMEM");
+    return !(e && e[0] == 'f' && e[2] == '3');
+  }();
+  if (a.lut_half && half_ok) return launch_ravu_impl<R, C, KEYMODE, NT, true>(a, device, stream);
+  return launch_ravu_impl<R, C, KEYMODE, NT, false>(a, device, stream);
 }
 
 }  // namespace
@@ -230,7 +260,7 @@ extern "C" int mpvp_ravu_launch(const mpvp_weights* lut, const mpvp_key_params* 
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   RavuArgs a{};
-  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.bucket = bucket_out;
+  a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
   a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;

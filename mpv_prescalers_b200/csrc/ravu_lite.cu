@@ -56,8 +56,25 @@ __device__ __forceinline__ constexpr bool ar_tap(int t) {
   return dx * dx + dy * dy <= 4;
 }
 
+// experiment knobs (tools/build_variant.py): defaults are the measured best
+#ifndef MPVP_X_PACKCONV_AR
+#define MPVP_X_PACKCONV_AR 0   // convolution sums as packed FFMA2 in the -ar kernels (FMA-pipe bound: no gain, 3.46 -> 3.60 ms)
+#endif
+#ifndef MPVP_X_AR3_BLOCKS
+#define MPVP_X_AR3_BLOCKS 2
+#endif
+#ifndef MPVP_X_AR3_P
+#define MPVP_X_AR3_P 2
+#endif
+#ifndef MPVP_X_AR3_STRIPS
+#define MPVP_X_AR3_STRIPS 5
+#endif
+
 constexpr int kTW = 64;       // tile width  (input pixels)
 constexpr int kThreads = 256; // 64 x 4 threads
+
+// acc + v * s with s broadcast to both lanes: one FFMA2 (the scalar rides in the instruction's .F32 operand form)
+__device__ __forceinline__ float2 fma2s(float2 v, float s, float2 acc) { return __ffma2_rn(v, make_float2(s, s), acc); }
 
 __device__ __forceinline__ float rgb_luma709(float r, float g, float b) {
   // dot(rgb, color_primary), left to right, no contraction (compute/ravu-3x-r2-rgb.hook:23,33)
@@ -97,7 +114,7 @@ __device__ __forceinline__ bool elect_one() {
 // 32 lanes gather 32 different LUT rows, so the gather is bank-conflict bound: 8-byte texels need half the
 // shared-memory wavefronts of 16-byte ones (68 vs 133 per 13-texel row on the config-2 planes).
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH>
-__global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : 2))
+__global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
   static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
@@ -262,7 +279,9 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
         };
 
         if constexpr (SCALE == 2) {
-          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+          // packed f32x2 accumulators (FFMA2 with a broadcast scalar operand): q01/q23 take the tap, the
+          // mirrored tap uses the same texel reversed (w.wzyx), so it accumulates into (phase 3, 2) / (1, 0)
+          float2 q01 = make_float2(0.f, 0.f), q23 = q01, m32 = q01, m10 = q01;
           // (hi, lo)[c] and (hi2, lo2)[c] as packed f32x2 accumulators: one FFMA2 updates both
           float2 hl[4], hl2[4];
           if constexpr (AR) {
@@ -274,10 +293,20 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
           for (int t = 0; t <= HALF; ++t) {
             const float4 w = texel(t);
             const float la = Wn(t / N, t % N);
-            r0 = fmaf(la, w.x, r0); r1 = fmaf(la, w.y, r1); r2 = fmaf(la, w.z, r2); r3 = fmaf(la, w.w, r3);
+            if constexpr (AR && !MPVP_X_PACKCONV_AR) {
+              q01.x = fmaf(la, w.x, q01.x); q01.y = fmaf(la, w.y, q01.y); q23.x = fmaf(la, w.z, q23.x); q23.y = fmaf(la, w.w, q23.y);
+            } else {
+              q01 = fma2s(make_float2(w.x, w.y), la, q01);
+              q23 = fma2s(make_float2(w.z, w.w), la, q23);
+            }
             if (t < HALF) {
               const float lb = Wn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
-              r0 = fmaf(lb, w.w, r0); r1 = fmaf(lb, w.z, r1); r2 = fmaf(lb, w.y, r2); r3 = fmaf(lb, w.x, r3);
+              if constexpr (AR && !MPVP_X_PACKCONV_AR) {
+                m32.x = fmaf(lb, w.x, m32.x); m32.y = fmaf(lb, w.y, m32.y); m10.x = fmaf(lb, w.z, m10.x); m10.y = fmaf(lb, w.w, m10.y);
+              } else {
+                m32 = fma2s(make_float2(w.x, w.y), lb, m32);
+                m10 = fma2s(make_float2(w.z, w.w), lb, m10);
+              }
             }
             if constexpr (AR) {
               if (ar_tap<R>(t)) {
@@ -304,14 +333,15 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
               }
             }
           }
-          float res[4] = {r0, r1, r2, r3};
+          float res[4] = {q01.x + m10.y, q01.y + m10.x, q23.x + m32.y, q23.y + m32.x};
           if constexpr (AR) {
             const float st = A.ar_strength;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float lov = 1.1f - __fdividef(hl2[c].y, hl[c].y);
-              const float hiv = __fdividef(hl2[c].x, hl[c].x) - 0.1f;
-              const float cl = fminf(fmaxf(res[c], lov), hiv);
+              // (hi2/hi - 0.1, 1.1 - lo2/lo)
+              const float2 q = __fmul2_rn(hl2[c], make_float2(__fdividef(1.0f, hl[c].x), __fdividef(1.0f, hl[c].y)));
+              const float2 hv = __ffma2_rn(q, make_float2(1.0f, -1.0f), make_float2(-0.1f, 1.1f));
+              const float cl = fminf(fmaxf(res[c], hv.y), hv.x);
               res[c] = res[c] * (1.0f - st) + cl * st;
             }
           } else {
@@ -333,20 +363,21 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
               if constexpr (C == 1) return l[p + j][i];
               else return s_tile[(1 + c) * PLANE + (ly0 + p + j) * SW + tx + i + (XO - O)];
             };
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01, ar32 = a01, ar10 = a01, br32 = a01, br10 = a01;
 #pragma unroll
             for (int t = 0; t <= HALF; ++t) {
               const float4 w0 = texel(2 * t), w1 = texel(2 * t + 1);
               const float la = Cn(t / N, t % N);
-              a0 = fmaf(la, w0.x, a0); a1 = fmaf(la, w0.y, a1); a2 = fmaf(la, w0.z, a2); a3 = fmaf(la, w0.w, a3);
-              b0 = fmaf(la, w1.x, b0); b1 = fmaf(la, w1.y, b1); b2 = fmaf(la, w1.z, b2); b3 = fmaf(la, w1.w, b3);
+              a01 = fma2s(make_float2(w0.x, w0.y), la, a01); a23 = fma2s(make_float2(w0.z, w0.w), la, a23);
+              b01 = fma2s(make_float2(w1.x, w1.y), la, b01); b23 = fma2s(make_float2(w1.z, w1.w), la, b23);
               if (t < HALF) {
                 const float lb = Cn((TAPS - 1 - t) / N, (TAPS - 1 - t) % N);
-                a0 = fmaf(lb, w1.w, a0); a1 = fmaf(lb, w1.z, a1); a2 = fmaf(lb, w1.y, a2); a3 = fmaf(lb, w1.x, a3);
-                b0 = fmaf(lb, w0.w, b0); b1 = fmaf(lb, w0.z, b1); b2 = fmaf(lb, w0.y, b2); b3 = fmaf(lb, w0.x, b3);
+                ar32 = fma2s(make_float2(w1.x, w1.y), lb, ar32); ar10 = fma2s(make_float2(w1.z, w1.w), lb, ar10);
+                br32 = fma2s(make_float2(w0.x, w0.y), lb, br32); br10 = fma2s(make_float2(w0.z, w0.w), lb, br10);
               }
             }
-            const float v[9] = {a0, a1, a2, a3, -1.f, b0, b1, b2, b3};
+            const float v[9] = {a01.x + ar10.y, a01.y + ar10.x, a23.x + ar32.y, a23.y + ar32.x, -1.f,
+                                b01.x + br10.y, b01.y + br10.x, b23.x + br32.y, b23.y + br32.x};
             float* __restrict__ o =
                 A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(3 * y) * A.out_sy + 3 * x;
 #pragma unroll
@@ -517,7 +548,7 @@ extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_par
     case 4: return launch_lite<2, false, 2, 4, 2>(a, lut->device, st);
     case 5: return launch_lite<2, true, 2, 4, 2>(a, lut->device, st);
     case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
-    case 7: return launch_lite<3, true, 2, 2, 3>(a, lut->device, st);  // 64x24 tiles: LUT + tiles + power tile, 2 CTAs/SM
+    case 7: return launch_lite<3, true, 2, MPVP_X_AR3_P, MPVP_X_AR3_STRIPS>(a, lut->device, st);  // 64x40 tiles: LUT + tiles + power tile = 103 KB, 2 CTAs/SM
     case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
     case 9: return launch_lite<4, true, 2, 2, 4>(a, lut->device, st);
   }
