@@ -82,6 +82,10 @@ extern "C" int mpvp_weights_create_lut(int device, const float* host, int w, int
   return MPVP_OK;
 }
 
+namespace mpvp {
+int nnedi3_group_size(int nns);  // nnedi3_tc.cu: which kernel (hence which B row order) serves this nns
+}
+
 extern "C" int mpvp_weights_create_nnedi3(int device, const float* w1, const float* w2, const float* b1,
                                           const float* b2, int nns, int win_short, mpvp_weights** out) {
   MPVP_REQUIRE(out, "out is null");
@@ -103,7 +107,8 @@ extern "C" int mpvp_weights_create_nnedi3(int device, const float* w1, const flo
   const int K = 8 * win_short;
   std::vector<unsigned char> packed;
   std::vector<float> bias, wf;
-  nnedi3_pack_host(w1, w2, b1, b2, nns, K, packed, bias, wf);
+  W->nn_group = nnedi3_group_size(nns);
+  nnedi3_pack_host(w1, w2, b1, b2, nns, K, W->nn_group, packed, bias, wf);
   W->nn_b_bytes = packed.size();
   cudaError_t e = cudaMalloc(&W->nn_b, packed.size());
   if (e == cudaSuccess) e = cudaMemcpy(W->nn_b, packed.data(), packed.size(), cudaMemcpyHostToDevice);

@@ -60,6 +60,7 @@ struct mpvp_weights {
   int lut_w = 0, lut_h = 0;
   // NNEDI3
   int nns = 0, win_short = 0;
+  int nn_group = 16;        // neurons per accumulator block in nn_b (16: 32-column blocks, 8: 16-column blocks)
   void* nn_b = nullptr;     // packed fp16 B operand(s) for tcgen05
   float* nn_bias = nullptr; // [2*nns] interleaved (b1*log2e, b2)
   float* nn_w = nullptr;    // fp32 copy [2*nns][K] (reference SIMT path / debugging)

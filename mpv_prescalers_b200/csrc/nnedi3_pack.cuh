@@ -20,7 +20,9 @@ namespace mpvp {
 
 // w1, w2: [nns][K]; outputs: packed B operand bytes, bias [2*nns] = (b1*log2e, b2) interleaved,
 // fp32 weights [2*nns][K] (unscaled, for the CUDA-core path)
-inline void nnedi3_pack_host(const float* w1, const float* w2, const float* b1, const float* b2, int nns, int K,
+// gn = neurons per accumulator block: 16 (32-column blocks, the layout described above) or 8 (16-column blocks:
+// row n' = 16*(n/8) + 8*which + n%8, for the pipelined kernel whose register staging is tcgen05.ld.x16)
+inline void nnedi3_pack_host(const float* w1, const float* w2, const float* b1, const float* b2, int nns, int K, int gn,
                              std::vector<unsigned char>& packed, std::vector<float>& bias, std::vector<float>& wf) {
   const float kLog2e = 1.4426950408889634f;
   const int N = 2 * nns;
@@ -29,7 +31,7 @@ inline void nnedi3_pack_host(const float* w1, const float* w2, const float* b1, 
   bias.resize(2 * (size_t)N);  // [0, N): tensor path (b1*log2e, b2); [N, 2N): CUDA-core path (b1, b2)
   wf.resize((size_t)N * K);
   for (int n = 0; n < nns; ++n) {
-    const int r1 = 32 * (n / 16) + (n % 16), r2 = r1 + 16;  // tensor-path rows of (W1_n, W2_n)
+    const int r1 = 2 * gn * (n / gn) + (n % gn), r2 = r1 + gn;  // tensor-path rows of (W1_n, W2_n)
     bias[r1] = b1[n] * kLog2e;
     bias[r2] = b2[n];
     bias[N + 2 * n] = b1[n];
