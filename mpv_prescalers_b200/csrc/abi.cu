@@ -73,6 +73,25 @@ extern "C" int mpvp_weights_create_lut(int device, const float* host, int w, int
     e = cudaMalloc(&W->lut_half, count * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemcpy(W->lut_half, hv.data(), count * sizeof(__half), cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess && round_to_fp16 && h == 288 * 9) {
+    // ravu-zoom LUT (//!FILTER LINEAR, ravu-zoom-r2.hook:135-139): a texture object lets the texture unit do the
+    // bilinear blend the GL sampler does in the reference
+    const cudaChannelFormatDesc cd = cudaCreateChannelDescHalf4();
+    e = cudaMallocArray(&W->lut_arr, &cd, (size_t)w, (size_t)h);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DToArray(W->lut_arr, 0, 0, W->lut_half, (size_t)w * 8, (size_t)w * 8, (size_t)h, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) {
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = W->lut_arr;
+      cudaTextureDesc td{};
+      td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModeLinear;
+      td.readMode = cudaReadModeElementType;
+      td.normalizedCoords = 0;
+      e = cudaCreateTextureObject(&W->lut_tex, &rd, &td, nullptr);
+    }
+  }
   if (e != cudaSuccess) {
     set_error("LUT upload failed: %s", cudaGetErrorString(e));
     mpvp_weights_destroy(W);
@@ -130,6 +149,8 @@ extern "C" int mpvp_weights_destroy(mpvp_weights* W) {
   DeviceGuard guard(W->device);
   if (W->lut) cudaFree(W->lut);
   if (W->lut_half) cudaFree(W->lut_half);
+  if (W->lut_tex) cudaDestroyTextureObject(W->lut_tex);
+  if (W->lut_arr) cudaFreeArray(W->lut_arr);
   if (W->nn_b) cudaFree(W->nn_b);
   if (W->nn_bias) cudaFree(W->nn_bias);
   if (W->nn_w) cudaFree(W->nn_w);

@@ -57,6 +57,8 @@ struct mpvp_weights {
   // LUT: rows x texels_per_row float4 (values already rounded to fp16 precision if requested)
   float* lut = nullptr;
   void* lut_half = nullptr;  // same texels as 4 x binary16 (exact when the LUT was rounded to fp16): halves L2 traffic
+  cudaArray_t lut_arr = nullptr;        // ravu-zoom LUTs only: the binary16 texels as a 2-D array behind a texture object
+  cudaTextureObject_t lut_tex = 0;      // FILTER LINEAR, clamp-to-edge, unnormalised coordinates
   int lut_w = 0, lut_h = 0;
   // NNEDI3
   int nns = 0, win_short = 0;

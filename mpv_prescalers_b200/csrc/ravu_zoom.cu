@@ -11,6 +11,8 @@
 // fp32 bilinear blend of four texels, at the same texel coordinates the GL sampler would use.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mpvp {
@@ -21,6 +23,7 @@ struct ZoomArgs {
   float* __restrict__ out;
   const void* __restrict__ lut;     // float4 texels, or 4 x binary16 texels (LUTH)
   const void* __restrict__ lut_ar;
+  cudaTextureObject_t tex, tex_ar;  // the same LUTs behind LINEAR-filtering texture objects (TEXF kernels)
   int32_t* __restrict__ bucket;  // [n][oh][ow] or null
   int n, h, w, oh, ow;
   int64_t in_sn, in_sc, in_sy, out_sn, out_sc, out_sy;
@@ -55,6 +58,7 @@ struct AxisEntry {
   int base;        // source texel index of window tap 0 minus the tile origin (filled by the caller)
   int i0, i0m;     // first LUT texel inside the 9-texel block: direct / mirrored
   float f, fm;     // blend weight of texel i0+1: direct / mirrored
+  float u, um;     // the same as continuous texel coordinates inside the block (texel centres at k + 0.5)
 };
 
 __device__ __forceinline__ AxisEntry axis_entry(int o, int O, int I, int groups) {
@@ -69,6 +73,7 @@ __device__ __forceinline__ AxisEntry axis_entry(int o, int O, int I, int groups)
   const float u0 = floorf(u), um0 = floorf(um);
   e.i0 = (int)u0; e.f = __fsub_rn(u, u0);
   e.i0m = (int)um0; e.fm = __fsub_rn(um, um0);
+  e.u = u + 0.5f; e.um = um + 0.5f;
   return e;
 }
 
@@ -85,7 +90,10 @@ __device__ __forceinline__ float4 lut_texel(const void* __restrict__ lut, int id
   }
 }
 
-template <int R, int C, int KEYMODE, bool AR, bool LUTH>
+// TEXF: the LUT fetch is ONE texture instruction (hardware bilinear blend of the four binary16 texels, exactly what
+// the reference's FILTER LINEAR sampler does, 8-bit blend weights: |error| <= 9e-5) instead of
+// four gathered loads and twelve FMAs.
+template <int R, int C, int KEYMODE, bool AR, bool LUTH, bool TEXF>
 __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ ZoomArgs A) {
   constexpr int N = 2 * R, TAPS = N * N, G = 4;
   constexpr int B = (TAPS / 2 + 3) / 4;   // LUT blocks per row group (2 for r2, 5 for r3)
@@ -198,13 +206,23 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
             r.w = t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
             return r;
           };
-          const float4 w4 = fetch(A.lut);
-          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          float4 w4;
           float av[4] = {0.f, 0.f, 0.f, 0.f};
-          if constexpr (AR) {
-            const float4 a4 = fetch(A.lut_ar);
-            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          if constexpr (TEXF) {
+            const float X = (float)(blk * 9) + (m ? ex.um : ex.u), Y = (float)(row * 9) + (m ? ey.um : ey.u);
+            w4 = tex2D<float4>(A.tex, X, Y);
+            if constexpr (AR) {
+              const float4 a4 = tex2D<float4>(A.tex_ar, X, Y);
+              av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            }
+          } else {
+            w4 = fetch(A.lut);
+            if constexpr (AR) {
+              const float4 a4 = fetch(A.lut_ar);
+              av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            }
           }
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int k = blk * 4 + e;
@@ -244,13 +262,13 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
   }
 }
 
-template <int R, int C, int KEYMODE, bool AR, bool LUTH>
+template <int R, int C, int KEYMODE, bool AR, bool LUTH, bool TEXF>
 int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   ZoomArgs a = a0;
   a.tiles_x = (a.ow + kTOW - 1) / kTOW;
   a.tiles_y = (a.oh + kTOH - 1) / kTOH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_zoom_kernel<R, C, KEYMODE, AR, LUTH>;
+  auto kern = ravu_zoom_kernel<R, C, KEYMODE, AR, LUTH, TEXF>;
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, 0));
   if (per_sm < 1) per_sm = 1;
@@ -265,8 +283,14 @@ int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
 
 template <int R, int C, int KEYMODE, bool AR>
 int launch_zoom(const ZoomArgs& a, int device, cudaStream_t stream, bool half_lut) {
-  if (half_lut) return launch_zoom_impl<R, C, KEYMODE, AR, true>(a, device, stream);
-  return launch_zoom_impl<R, C, KEYMODE, AR, false>(a, device, stream);
+  // MPVP_ZOOM_TEX=0: explicit fp32 blend of four loaded texels instead of the texture unit (A/B switch)
+  static const bool tex_ok = [] {
+    const char* e = getenv("MPVP_ZOOM_TEX");
+    return !(e && e[0] == '0');
+  }();
+  if (half_lut && tex_ok && a.tex && (!AR || a.tex_ar)) return launch_zoom_impl<R, C, KEYMODE, AR, true, true>(a, device, stream);
+  if (half_lut) return launch_zoom_impl<R, C, KEYMODE, AR, true, false>(a, device, stream);
+  return launch_zoom_impl<R, C, KEYMODE, AR, false, false>(a, device, stream);
 }
 
 }  // namespace
@@ -301,6 +325,8 @@ extern "C" int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights
   const bool half_lut = lut->lut_half && (!lut_ar || lut_ar->lut_half);
   a.lut = half_lut ? lut->lut_half : static_cast<const void*>(lut->lut);
   a.lut_ar = lut_ar ? (half_lut ? lut_ar->lut_half : static_cast<const void*>(lut_ar->lut)) : nullptr;
+  a.tex = lut->lut_tex;
+  a.tex_ar = lut_ar ? lut_ar->lut_tex : 0;
   a.n = n; a.h = h; a.w = w; a.oh = out_h; a.ow = out_w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;
   a.out_sn = out_stride_n; a.out_sc = out_stride_c; a.out_sy = out_stride_y;
