@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
   __shared__ AxisEntry s_ax[kTOW], s_ay[kTOH];
 
   const int tid = threadIdx.x;
-  const int tx = tid % kTOW, ty = tid / kTOW;
+  static_assert(kTOW == 32 && kTOH == 32 && kNT == 256, "the patch mapping below assumes 32x32 tiles and 8 warps");
 
   for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
     const int tix = (int)(tile % A.tiles_x);
@@ -167,14 +167,16 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     }
     __syncthreads();
 
-    const int ox = ox0 + tx;
-    if (ox >= A.ow) continue;
-    const AxisEntry ex = s_ax[tx];
+    // A warp covers an 8x4 patch of output pixels, not a 32x1 row segment: the LUT fetch is bound by the number of
+    // distinct texel neighbourhoods per texture instruction, and a compact patch spans 3-4 times fewer source cells
+    // (hence LUT row groups) than a row segment does.
 #pragma unroll 1
     for (int rr = 0; rr < RPT; ++rr) {
-      const int ly = ty + rr * (kNT / kTOW);
-      const int oy = oy0 + ly;
-      if (oy >= A.oh) break;
+      const int patch = rr * (kNT / 32) + (tid >> 5);           // 4 patches across, 8 down
+      const int lx = (patch & 3) * 8 + (tid & 7), ly = (patch >> 2) * 4 + ((tid >> 3) & 3);
+      const int ox = ox0 + lx, oy = oy0 + ly;
+      if (ox >= A.ow || oy >= A.oh) continue;
+      const AxisEntry ex = s_ax[lx];
       const AxisEntry ey = s_ay[ly];
       const int row = s_key[ey.base * CW + ex.base];
       if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
