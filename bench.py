@@ -102,12 +102,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
-def algorithmic_work(wl, n_frames):
+IO_MODES = {  # name: (input bytes / sample, output bytes / sample)
+    "f32": (4, 4), "u8": (1, 1), "u10": (2, 2), "f16out": (4, 2),
+}
+
+
+def algorithmic_work(wl, n_frames, io="f32"):
     """(output Mpix, algorithmic bytes, algorithmic flops) of one step on one GPU."""
     hook, c, h, w, _, fac, _ = WORKLOADS[wl]
     oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
     out_px = n_frames * oh * ow
-    nbytes = 4.0 * c * n_frames * (h * w + oh * ow)
+    bi, bo = IO_MODES[io]
+    nbytes = 1.0 * c * n_frames * (bi * h * w + bo * oh * ow)
     flops = 0.0
     if hook.startswith("nnedi3"):
         import re
@@ -193,6 +199,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ravu-lite-ar-r3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--io", default="f32", choices=["f32", "u8", "u10", "f16out"],
+                    help="plane formats either side of the path: f32 (BASELINE.json's), u8 / u10 = UNORM video planes in "
+                         "and out (uint8, 10 bits in uint16), f16out = float32 in, binary16 out (SURVEY.md 8f rank 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -205,10 +214,10 @@ def main():
     nf = args.frames or nf_default
     oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
     config = {
-        "workload": f"{hook} {w}x{h}->{ow}x{oh} {'luma' if c == 1 else '3ch'} fp32, {nf} frames per GPU (BASELINE.json configs[{cfg_idx}])",
+        "workload": f"{hook} {w}x{h}->{ow}x{oh} {'luma' if c == 1 else '3ch'} {'fp32' if args.io == 'f32' else 'planes ' + args.io}, {nf} frames per GPU (BASELINE.json configs[{cfg_idx}])",
         "frames_per_gpu": nf,
         "parallelism": f"frame-sharded x{world}, no collective",
-        "l2": "working set per step exceeds the 126 MB L2" if 4.0 * c * nf * (h * w + oh * ow) > 2.5e8 else "L2 flushed between steps",
+        "l2": "working set per step exceeds the 126 MB L2" if 1.0 * c * nf * (IO_MODES[args.io][0] * h * w + IO_MODES[args.io][1] * oh * ow) > 2.5e8 else "L2 flushed between steps",
     }
 
     if args.impl == "reference":
@@ -255,13 +264,24 @@ def main():
     pl = plan(hk, (h, w), out_size)
     W = upload_weights(hk, local_rank)
     x = torch_batch(nf, c, h, w, dev, seed=1000 * cfg_idx + rank)
+    from mpv_prescalers_b200.api import PlaneIO
+
+    io_kw = {}
+    if args.io == "u8":
+        x = torch.round(x.clamp(0, 1) * 255.0).to(torch.uint8)
+    elif args.io == "u10":
+        x = torch.round(x.clamp(0, 1) * 1023.0).to(torch.int32).to(torch.uint16)
+        io_kw = dict(bit_depth=10)
+    elif args.io == "f16out":
+        io_kw = dict(out_dtype=torch.float16)
+    pio = PlaneIO(x.dtype, io_kw.get("out_dtype"), io_kw.get("bit_depth"))
     lib = _native.lib()
     flush = None
     if "flushed" in config["l2"]:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        out, _ = _launch(hk, pl, x, W, False)
+        out, _ = _launch(hk, pl, x, W, False, pio)
         return out
 
     def barrier():
@@ -295,7 +315,7 @@ def main():
     total_ms = sum(kernel_ms)
     total_ms = max_over_ranks(total_ms, dev)
     ms_per_step = total_ms / args.steps
-    mpix, abytes, aflops = algorithmic_work(wl, nf)
+    mpix, abytes, aflops = algorithmic_work(wl, nf, args.io)
     value = mpix * world / (ms_per_step / 1e3)
 
     hbm_peak, tc_peak, src = peaks()
@@ -312,7 +332,7 @@ def main():
     if os.path.exists(tr):
         try:
             with open(tr) as f:
-                roof["traffic"] = json.load(f).get(wl)
+                roof["traffic"] = json.load(f).get(wl) if args.io == "f32" else None
         except Exception:
             pass
 
@@ -321,17 +341,17 @@ def main():
     if not args.no_e2e:
         xh = x.cpu().pin_memory()
         e2e_steps = max(1, min(args.steps, 3))
-        oh_pinned = torch.empty((nf, c, oh, ow), dtype=torch.float32, pin_memory=True)
-        o = prescale(xh, hk, out_size, out=oh_pinned)  # warm-up (allocator pools, streams)
+        oh_pinned = torch.empty((nf, c, oh, ow), dtype=pio.out_dtype, pin_memory=True)
+        o = prescale(xh, hk, out_size, out=oh_pinned, **io_kw)  # warm-up (allocator pools, streams)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            o = prescale(xh, hk, out_size, out=oh_pinned)
+            o = prescale(xh, hk, out_size, out=oh_pinned, **io_kw)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt = max_over_ranks(dt, dev)
-        e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * 4),
-               "d2h_bytes_per_step": int(o.numel() * 4), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
+        e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
+               "d2h_bytes_per_step": int(o.numel() * o.element_size()), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
         del o, xh, oh_pinned
 
     cpu = None
@@ -345,7 +365,7 @@ def main():
         line = {
             "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "data": "synthetic", "config": dict(config, io=args.io), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line))

@@ -77,6 +77,25 @@ typedef struct mpvp_key_params {
 #define MPVP_KEY_YUV 1  /* 3 channels, key from channel 0              (ravu-r2-yuv.hook)  */
 #define MPVP_KEY_RGB 2  /* 3 channels, key from BT.709 luma of rgb     (ravu-r2-rgb.hook:21) */
 
+/* ---- plane formats (the wire formats either side of the path) -------------------
+ * The reference's shaders never see integers: the host binds 8/10/16-bit video planes as UNORM textures,
+ * `HOOKED_tex()` returns HOOKED_mul * texture(HOOKED_raw, pos) (gather/ravu-lite-ar-r3.hook:23), and the
+ * pass output goes to the host's FBO format (rgba16f by default) or, for the last pass, to the output surface.
+ * The *_io entry points take and produce those formats directly, so integer video never round-trips HBM as
+ * float32:  integer input   sample = float(raw) / in_max   (one correctly rounded fp32 division; in_max = 255,
+ *                           1023, 65535 ... = UNORM normalisation times HOOKED_mul);
+ *           integer output  raw = rint(clamp(v, 0, 1) * out_max)  (round-half-even, the UNORM store rule);
+ *           MPVP_FMT_F16    binary16 planes (round-to-nearest-even on store).
+ * Strides are always in ELEMENTS of the plane's own type.  A null `io` means float32 in and out. */
+#define MPVP_FMT_F32 0
+#define MPVP_FMT_F16 1
+#define MPVP_FMT_U8 2
+#define MPVP_FMT_U16 3
+typedef struct mpvp_io {
+  int32_t in_format, out_format; /* MPVP_FMT_* */
+  float in_max, out_max;         /* integer formats only: 255, 1023, 4095, 65535 ... */
+} mpvp_io;
+
 const char* mpvp_last_error(void);
 int mpvp_abi_version(void);
 /* number of kernels launched by this library since load (all threads); for bench bookkeeping */
@@ -134,6 +153,33 @@ int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights* lut_ar,
 int mpvp_nnedi3_launch(const mpvp_weights* nn, int direction, const float* in, float* out, int n,
                        int h, int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
                        int64_t out_stride_y, void* stream);
+
+/* ---- the same launches with explicit plane formats (see mpvp_io above) ------------------------------------------
+ * `in` / `out` point to planes of io->in_format / io->out_format; everything else is as in the float32 entry
+ * points, which are exactly these with io = NULL. */
+int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                             float ar_strength, const void* in, void* out, int n, int h, int w,
+                             int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                             int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io, void* stream);
+int mpvp_ravu_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                        const void* in, void* out, int n, int h, int w, int64_t in_stride_n,
+                        int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                        int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io,
+                        void* stream);
+int mpvp_ravu3x_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                          const void* in, void* out, int n, int h, int w, int64_t in_stride_n,
+                          int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                          int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io,
+                          void* stream);
+int mpvp_ravu_zoom_launch_io(const mpvp_weights* lut, const mpvp_weights* lut_ar,
+                             const mpvp_key_params* key, int radius, int key_mode, float ar_strength,
+                             const void* in, void* out, int n, int h, int w, int out_h, int out_w,
+                             int64_t in_stride_n, int64_t in_stride_c, int64_t in_stride_y,
+                             int64_t out_stride_n, int64_t out_stride_c, int64_t out_stride_y,
+                             int32_t* bucket_out, const mpvp_io* io, void* stream);
+int mpvp_nnedi3_launch_io(const mpvp_weights* nn, int direction, const void* in, void* out, int n, int h,
+                          int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                          int64_t out_stride_y, const mpvp_io* io, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end path: H2D + kernel + D2H inside the call) --------- */
 int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,

@@ -90,11 +90,20 @@ class KeyParams(ctypes.Structure):
     ]
 
 
+class IoDesc(ctypes.Structure):
+    """mpvp_io: plane formats either side of a launch (include/mpvp.h)."""
+
+    _fields_ = [("in_format", ctypes.c_int32), ("out_format", ctypes.c_int32), ("in_max", ctypes.c_float), ("out_max", ctypes.c_float)]
+
+
+FMT_F32, FMT_F16, FMT_U8, FMT_U16 = 0, 1, 2, 3
+
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
 _kp = ctypes.POINTER(KeyParams)
+_iop = ctypes.POINTER(IoDesc)
 
 # name -> (restype, argtypes): must list every symbol include/mpvp.h declares
 SIGNATURES = {
@@ -109,6 +118,11 @@ SIGNATURES = {
     "mpvp_ravu3x_launch": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "mpvp_ravu_zoom_launch": (_i, [_vp, _vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "mpvp_nnedi3_launch": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
+    "mpvp_ravu_lite_launch_io": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
+    "mpvp_ravu_launch_io": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
+    "mpvp_ravu3x_launch_io": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
+    "mpvp_ravu_zoom_launch_io": (_i, [_vp, _vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
+    "mpvp_nnedi3_launch_io": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _iop, _vp]),
     "mpvp_ravu_lite_host": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i]),
 }
 

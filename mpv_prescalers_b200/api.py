@@ -224,8 +224,61 @@ def clear_weight_cache() -> None:
 # ----------------------------------------------------------------------------------------------
 
 
-def _launch(hook: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, want_buckets: bool):
-    """x: float32 CUDA tensor [N, C, H, W] contiguous in (H, W).  Returns (out, buckets|None)."""
+_FMT_OF = {torch.float32: _native.FMT_F32, torch.float16: _native.FMT_F16, torch.uint8: _native.FMT_U8, torch.uint16: _native.FMT_U16}
+
+
+class PlaneIO:
+    """Plane formats either side of the path (``mpvp_io`` in include/mpvp.h).
+
+    Integer planes are UNORM video planes: a raw sample r of a ``bit_depth``-bit plane stands for
+    ``r / (2**bit_depth - 1)`` -- the host's texture normalisation times ``HOOKED_mul``
+    (gather/ravu-lite-ar-r3.hook:23) -- and an integer result is ``rint(clamp(v, 0, 1) * (2**bit_depth - 1))``.
+    float16 stands for the rgba16f FBO precision mpv keeps between passes."""
+
+    def __init__(self, in_dtype=torch.float32, out_dtype=None, bit_depth: Optional[int] = None, out_bit_depth: Optional[int] = None):
+        out_dtype = in_dtype if out_dtype is None else out_dtype
+        for d in (in_dtype, out_dtype):
+            if d not in _FMT_OF:
+                raise TypeError(f"plane dtype {d} not supported (float32, float16, uint8, uint16)")
+        self.in_dtype, self.out_dtype = in_dtype, out_dtype
+
+        def depth(dt, bits, what):
+            if dt not in (torch.uint8, torch.uint16):
+                return 0
+            full = 8 if dt == torch.uint8 else 16
+            bits = full if bits is None else int(bits)
+            if not 1 <= bits <= full:
+                raise ValueError(f"{what} {bits} does not fit {dt}")
+            return bits
+
+        self.in_bits = depth(in_dtype, bit_depth, "bit_depth")
+        if out_bit_depth is None and out_dtype in (torch.uint8, torch.uint16):
+            out_bit_depth = self.in_bits if (self.in_bits and self.in_bits <= (8 if out_dtype == torch.uint8 else 16)) else None
+        self.out_bits = depth(out_dtype, out_bit_depth, "out_bit_depth")
+        self.in_max = float((1 << self.in_bits) - 1) if self.in_bits else 1.0
+        self.out_max = float((1 << self.out_bits) - 1) if self.out_bits else 1.0
+
+    @property
+    def is_default(self) -> bool:
+        return self.in_dtype == torch.float32 and self.out_dtype == torch.float32
+
+    def desc(self, first: bool = True, last: bool = True) -> "_native.IoDesc":
+        """mpvp_io of one launch of a chain: only the first launch reads in_dtype, only the last writes out_dtype
+        (NNEDI3's W x 2H image between its two launches stays float32)."""
+        return _native.IoDesc(
+            _FMT_OF[self.in_dtype] if first else _native.FMT_F32, _FMT_OF[self.out_dtype] if last else _native.FMT_F32,
+            self.in_max if first else 1.0, self.out_max if last else 1.0)
+
+
+_IO_F32 = PlaneIO()
+
+
+def _launch(hook: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, want_buckets: bool, io: Optional[PlaneIO] = None):
+    """x: CUDA tensor [N, C, H, W] (dtype io.in_dtype) contiguous in (H, W).  Returns (out, buckets|None)."""
+    io = _IO_F32 if io is None else io
+    if x.dtype != io.in_dtype:
+        raise TypeError(f"frames are {x.dtype}, the plane format says {io.in_dtype}")
+    iod = io.desc()
     lib = _native.lib()
     v = hook.variant
     dev = x.device.index
@@ -237,52 +290,53 @@ def _launch(hook: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, want_buckets
     bptr = None
 
     def out_tensor(hh, ww):
-        return torch.empty((n, c, hh, ww), dtype=torch.float32, device=x.device)
+        return torch.empty((n, c, hh, ww), dtype=io.out_dtype, device=x.device)
 
     if v.family == "ravu-lite":
         out = out_tensor(oh, ow)
         if want_buckets:
             bk = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
             bptr = bk.data_ptr()
-        rc = lib.mpvp_ravu_lite_launch(
+        rc = lib.mpvp_ravu_lite_launch_io(
             W.handles["lut"], ctypes.byref(W.key), v.radius, 1 if v.ar else 0, float(v.ar_strength),
-            x.data_ptr(), out.data_ptr(), n, h, w, x.stride(0), x.stride(2), out.stride(0), out.stride(2), bptr, stream)
-        _native.check(rc, "mpvp_ravu_lite_launch")
+            x.data_ptr(), out.data_ptr(), n, h, w, x.stride(0), x.stride(2), out.stride(0), out.stride(2), bptr,
+            ctypes.byref(iod), stream)
+        _native.check(rc, "mpvp_ravu_lite_launch_io")
         return out, bk
     if v.family in ("ravu", "ravu-3x"):
         out = out_tensor(oh, ow)
         if want_buckets:
             bk = torch.empty((n, 3, h, w) if v.family == "ravu" else (n, h, w), dtype=torch.int32, device=x.device)
             bptr = bk.data_ptr()
-        fn = lib.mpvp_ravu_launch if v.family == "ravu" else lib.mpvp_ravu3x_launch
+        fn = lib.mpvp_ravu_launch_io if v.family == "ravu" else lib.mpvp_ravu3x_launch_io
         rc = fn(W.handles["lut"], ctypes.byref(W.key), v.radius, key_mode, x.data_ptr(), out.data_ptr(), n, h, w,
-                x.stride(0), x.stride(1), x.stride(2), out.stride(0), out.stride(1), out.stride(2), bptr, stream)
-        _native.check(rc, "mpvp_ravu_launch" if v.family == "ravu" else "mpvp_ravu3x_launch")
+                x.stride(0), x.stride(1), x.stride(2), out.stride(0), out.stride(1), out.stride(2), bptr,
+                ctypes.byref(iod), stream)
+        _native.check(rc, "mpvp_ravu_launch_io" if v.family == "ravu" else "mpvp_ravu3x_launch_io")
         return out, bk
     if v.family == "ravu-zoom":
         out = out_tensor(oh, ow)
         if want_buckets:
             bk = torch.empty((n, oh, ow), dtype=torch.int32, device=x.device)
             bptr = bk.data_ptr()
-        rc = lib.mpvp_ravu_zoom_launch(
+        rc = lib.mpvp_ravu_zoom_launch_io(
             W.handles["lut"], W.handles.get("lut_ar"), ctypes.byref(W.key), v.radius, key_mode, float(v.ar_strength),
             x.data_ptr(), out.data_ptr(), n, h, w, oh, ow, x.stride(0), x.stride(1), x.stride(2),
-            out.stride(0), out.stride(1), out.stride(2), bptr, stream)
-        _native.check(rc, "mpvp_ravu_zoom_launch")
+            out.stride(0), out.stride(1), out.stride(2), bptr, ctypes.byref(iod), stream)
+        _native.check(rc, "mpvp_ravu_zoom_launch_io")
         return out, bk
     if v.family == "nnedi3":
         cur = x.reshape(n * c, h, w)
-        if pl.double_y:
-            nxt = torch.empty((n * c, 2 * cur.shape[1], cur.shape[2]), dtype=torch.float32, device=x.device)
-            rc = lib.mpvp_nnedi3_launch(W.handles["y"], 0, cur.data_ptr(), nxt.data_ptr(), cur.shape[0], cur.shape[1], cur.shape[2],
-                                        cur.stride(0), cur.stride(1), nxt.stride(0), nxt.stride(1), stream)
-            _native.check(rc, "mpvp_nnedi3_launch(y)")
-            cur = nxt
-        if pl.double_x:
-            nxt = torch.empty((n * c, cur.shape[1], 2 * cur.shape[2]), dtype=torch.float32, device=x.device)
-            rc = lib.mpvp_nnedi3_launch(W.handles["x"], 1, cur.data_ptr(), nxt.data_ptr(), cur.shape[0], cur.shape[1], cur.shape[2],
-                                        cur.stride(0), cur.stride(1), nxt.stride(0), nxt.stride(1), stream)
-            _native.check(rc, "mpvp_nnedi3_launch(x)")
+        passes = [d for d, on in ((0, pl.double_y), (1, pl.double_x)) if on]
+        for k, d in enumerate(passes):
+            first, last = k == 0, k == len(passes) - 1
+            shape = (n * c, 2 * cur.shape[1], cur.shape[2]) if d == 0 else (n * c, cur.shape[1], 2 * cur.shape[2])
+            nxt = torch.empty(shape, dtype=io.out_dtype if last else torch.float32, device=x.device)
+            pio = io.desc(first, last)
+            rc = lib.mpvp_nnedi3_launch_io(W.handles["y" if d == 0 else "x"], d, cur.data_ptr(), nxt.data_ptr(), cur.shape[0],
+                                           cur.shape[1], cur.shape[2], cur.stride(0), cur.stride(1), nxt.stride(0), nxt.stride(1),
+                                           ctypes.byref(pio), stream)
+            _native.check(rc, f"mpvp_nnedi3_launch_io({'y' if d == 0 else 'x'})")
             cur = nxt
         return cur.reshape(n, c, cur.shape[1], cur.shape[2]), None
     raise HookError(f"unsupported family {v.family}")
@@ -291,8 +345,8 @@ def _launch(hook: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, want_buckets
 def _normalise_input(frames: torch.Tensor, v: Variant) -> Tuple[torch.Tensor, Tuple[int, ...]]:
     if not isinstance(frames, torch.Tensor):
         raise TypeError("frames must be a torch.Tensor")
-    if frames.dtype != torch.float32:
-        raise TypeError(f"frames must be float32 in [0, 1] (got {frames.dtype})")
+    if frames.dtype not in _FMT_OF:
+        raise TypeError(f"frames must be float32 / float16 in [0, 1] or uint8 / uint16 video planes (got {frames.dtype})")
     shape = tuple(frames.shape)
     c = v.channels
     if c == 1:
@@ -335,6 +389,9 @@ def prescale(
     return_buckets: bool = False,
     is_yuv: bool = True,
     out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    bit_depth: Optional[int] = None,
+    out_bit_depth: Optional[int] = None,
 ):
     """Apply one mpv-prescalers hook file to a batch of frames.
 
@@ -348,8 +405,13 @@ def prescale(
     devices       shard the batch dimension over these GPUs (frames are independent, no collective);
                   returns a list with one output tensor per device (outputs stay on their GPU).
     lut_precision 'fp16' reproduces the reference's rgba16f LUT storage; 'fp32' keeps the file's floats.
-    out           optional destination for CPU inputs: a (pinned) float32 CPU tensor ``[N,C,OH,OW]`` that
-                  receives the result, so that a video loop does not re-allocate pinned memory per batch.
+    out           optional destination for CPU inputs: a (pinned) CPU tensor ``[N,C,OH,OW]`` of the output dtype
+                  that receives the result, so that a video loop does not re-allocate pinned memory per batch.
+    out_dtype     dtype of the result (default: the dtype of ``frames``).  Besides float32 the path reads and writes
+                  the wire formats of video directly: uint8 / uint16 UNORM planes (``bit_depth`` significant bits,
+                  e.g. 10 for 10-bit video in 16-bit containers; a raw sample r means r / (2**bit_depth - 1), the
+                  host's texture normalisation times ``HOOKED_mul``) and float16 (mpv's rgba16f FBO precision).
+                  Integer results are ``rint(clamp(v, 0, 1) * (2**out_bit_depth - 1))``.
 
     Returns the output tensor (same rank as the input) carrying ``.offset`` (accumulated ``//!OFFSET``,
     (x, y) in output pixels), ``.applied`` and ``.plan``; with ``return_buckets=True`` a pair
@@ -360,9 +422,11 @@ def prescale(
     if devices is not None:
         from .sharding import prescale_sharded
 
-        return prescale_sharded(frames, hk, output_size, list(devices), lut_precision, is_yuv)
+        return prescale_sharded(frames, hk, output_size, list(devices), lut_precision, is_yuv,
+                                out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
     x, in_shape = _normalise_input(frames, v)
     n, c, h, w = x.shape
+    io = PlaneIO(x.dtype, out_dtype, bit_depth, out_bit_depth)
     pl = plan(hk, (h, w), output_size, is_yuv)
     if not pl.applied:
         out = frames
@@ -374,13 +438,13 @@ def prescale(
     if host_input:
         dev = torch.device("cuda", torch.cuda.current_device())
         W = upload_weights(hk, dev.index, lut_precision)
-        res, bk = _prescale_host(hk, pl, x, W, dev, return_buckets, out)
+        res, bk = _prescale_host(hk, pl, x, W, dev, return_buckets, out, io)
     else:
         dev = x.device
         xd = x if (x.stride(3) == 1 and x.stride(2) >= w) else x.contiguous()
         W = upload_weights(hk, dev.index, lut_precision)
         with torch.cuda.device(dev):
-            res, bk = _launch(hk, pl, xd, W, return_buckets)
+            res, bk = _launch(hk, pl, xd, W, return_buckets, io)
     res = _restore_shape(res, in_shape, c)
     res.offset, res.applied, res.plan = pl.offset, True, pl
     return (res, bk) if return_buckets else res
@@ -390,7 +454,7 @@ _host_streams: Dict[int, List[torch.cuda.Stream]] = {}
 
 
 def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: torch.device, want_buckets: bool,
-                   out: Optional[torch.Tensor]):
+                   out: Optional[torch.Tensor], io: Optional["PlaneIO"] = None):
     """CPU tensor in, CPU tensor out: frames are staged through the GPU in chunks on two streams so that the
     host->device copy of chunk k+1 and the device->host copy of chunk k-1 overlap the kernel of chunk k
     (effective only with pinned host memory)."""
@@ -399,17 +463,18 @@ def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: to
     if hk.variant.family == "nnedi3":
         oh, ow = h * (2 if pl.double_y else 1), w * (2 if pl.double_x else 1)
     x = x.contiguous()
+    io = _IO_F32 if io is None else io
     if out is None:
-        out = torch.empty((n, c, oh, ow), dtype=torch.float32, pin_memory=True)
-    elif tuple(out.shape) != (n, c, oh, ow) or out.dtype != torch.float32 or out.device.type != "cpu":
-        raise ValueError(f"out must be a float32 CPU tensor of shape {(n, c, oh, ow)}")
+        out = torch.empty((n, c, oh, ow), dtype=io.out_dtype, pin_memory=True)
+    elif tuple(out.shape) != (n, c, oh, ow) or out.dtype != io.out_dtype or out.device.type != "cpu":
+        raise ValueError(f"out must be a {io.out_dtype} CPU tensor of shape {(n, c, oh, ow)}")
     bks = torch.empty((n,) + _bucket_shape(hk.variant, h, w, oh, ow), dtype=torch.int32) if want_buckets else None
     if bks is not None and hk.variant.family == "nnedi3":
         bks = None
     streams = _host_streams.get(dev.index)
     if streams is None:
         streams = _host_streams[dev.index] = [torch.cuda.Stream(dev) for _ in range(2)]
-    frame_bytes = 4 * c * (h * w + oh * ow)
+    frame_bytes = c * (x.element_size() * h * w + out.element_size() * oh * ow)
     chunk = max(1, min(n, (256 << 20) // max(frame_bytes, 1)))
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
@@ -420,7 +485,7 @@ def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: to
             s = streams[k & 1]
             with torch.cuda.stream(s):
                 xd = x[f0:f1].to(dev, non_blocking=True)
-                od, bd = _launch(hk, pl, xd, W, want_buckets and bks is not None)
+                od, bd = _launch(hk, pl, xd, W, want_buckets and bks is not None, io)
                 out[f0:f1].copy_(od, non_blocking=True)
                 if bd is not None:
                     bks[f0:f1].copy_(bd, non_blocking=True)

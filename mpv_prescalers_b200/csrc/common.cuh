@@ -1,6 +1,7 @@
 // Shared host/device helpers for libmpvp (sm_100a).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -279,6 +280,72 @@ __device__ __forceinline__ int ravu_key2(const mpvp_key_params& kp, WF W) {
 __device__ __forceinline__ float pow32(float c) {
   c *= c; c *= c; c *= c; c *= c; c *= c;
   return c;
+}
+
+// ---- plane formats (mpvp_io) --------------------------------------------------------------------------------
+// One load site (tile staging, once per source pixel) and one store site per kernel go through these; the format
+// is warp-uniform, so the switch costs a uniform branch.
+struct IoFmt {
+  int in_fmt = MPVP_FMT_F32, out_fmt = MPVP_FMT_F32;
+  float in_max = 1.0f, out_max = 1.0f;
+};
+
+inline int parse_io(const mpvp_io* io, IoFmt& f) {
+  f = IoFmt{};
+  if (!io) return MPVP_OK;
+  MPVP_REQUIRE(io->in_format >= MPVP_FMT_F32 && io->in_format <= MPVP_FMT_U16, "bad in_format %d", io->in_format);
+  MPVP_REQUIRE(io->out_format >= MPVP_FMT_F32 && io->out_format <= MPVP_FMT_U16, "bad out_format %d", io->out_format);
+  f.in_fmt = io->in_format; f.out_fmt = io->out_format;
+  if (f.in_fmt >= MPVP_FMT_U8) {
+    MPVP_REQUIRE(io->in_max >= 1.0f && io->in_max <= (f.in_fmt == MPVP_FMT_U8 ? 255.0f : 65535.0f), "bad in_max %g", io->in_max);
+    f.in_max = io->in_max;
+  }
+  if (f.out_fmt >= MPVP_FMT_U8) {
+    MPVP_REQUIRE(io->out_max >= 1.0f && io->out_max <= (f.out_fmt == MPVP_FMT_U8 ? 255.0f : 65535.0f), "bad out_max %g", io->out_max);
+    f.out_max = io->out_max;
+  }
+  return MPVP_OK;
+}
+__host__ __device__ __forceinline__ int fmt_bytes(int fmt) { return fmt == MPVP_FMT_F32 ? 4 : (fmt == MPVP_FMT_U8 ? 1 : 2); }
+
+// sample `off` (in elements) of a plane of format fmt, as the shader's HOOKED_tex() would return it
+__device__ __forceinline__ float load_px(const void* __restrict__ p, int64_t off, int fmt, float in_max) {
+  switch (fmt) {
+    case MPVP_FMT_F32: return __ldg(static_cast<const float*>(p) + off);
+    case MPVP_FMT_F16: return __half2float(__ldg(static_cast<const __half*>(p) + off));
+    case MPVP_FMT_U8: return __fdiv_rn((float)__ldg(static_cast<const unsigned char*>(p) + off), in_max);
+    default: return __fdiv_rn((float)__ldg(static_cast<const unsigned short*>(p) + off), in_max);
+  }
+}
+__device__ __forceinline__ unsigned int quant_px(float v, float out_max) {
+  return __float2uint_rn(fminf(fmaxf(v, 0.0f), 1.0f) * out_max);
+}
+// one pixel at element offset off (streaming store)
+__device__ __forceinline__ void store_px(void* __restrict__ p, int64_t off, float v, int fmt, float out_max) {
+  switch (fmt) {
+    case MPVP_FMT_F32: __stcs(static_cast<float*>(p) + off, v); break;
+    case MPVP_FMT_F16: __stcs(reinterpret_cast<unsigned short*>(p) + off, __half_as_ushort(__float2half_rn(v))); break;
+    case MPVP_FMT_U8: __stcs(static_cast<unsigned char*>(p) + off, (unsigned char)quant_px(v, out_max)); break;
+    default: __stcs(static_cast<unsigned short*>(p) + off, (unsigned short)quant_px(v, out_max)); break;
+  }
+}
+// two horizontally adjacent pixels at an EVEN element offset (one vector store)
+__device__ __forceinline__ void store_px2(void* __restrict__ p, int64_t off, float a, float b, int fmt, float out_max) {
+  switch (fmt) {
+    case MPVP_FMT_F32: __stcs(reinterpret_cast<float2*>(static_cast<float*>(p) + off), make_float2(a, b)); break;
+    case MPVP_FMT_F16: {
+      const __half2 h = __floats2half2_rn(a, b);
+      __stcs(reinterpret_cast<unsigned int*>(static_cast<__half*>(p) + off), *reinterpret_cast<const unsigned int*>(&h));
+      break;
+    }
+    case MPVP_FMT_U8:
+      __stcs(reinterpret_cast<unsigned short*>(static_cast<unsigned char*>(p) + off),
+             (unsigned short)(quant_px(a, out_max) | (quant_px(b, out_max) << 8)));
+      break;
+    default:
+      __stcs(reinterpret_cast<unsigned int*>(static_cast<unsigned short*>(p) + off), quant_px(a, out_max) | (quant_px(b, out_max) << 16));
+      break;
+  }
 }
 
 __host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

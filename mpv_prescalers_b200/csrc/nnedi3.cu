@@ -144,8 +144,9 @@ int nnedi3_simt(const mpvp_weights* nn, int direction, const float* in, float* o
   return direction == 0 ? launch_simt<6, 0>(a, nn->device, st) : launch_simt<6, 1>(a, nn->device, st);
 }
 
-int nnedi3_tc(const mpvp_weights* nn, int direction, const float* in, float* out, int n, int h, int w,
-              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, cudaStream_t st);
+int nnedi3_tc(const mpvp_weights* nn, int direction, const void* in, void* out, int n, int h, int w,
+              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, const IoFmt& io,
+              cudaStream_t st);
 
 // MPVP_NNEDI3_IMPL=simt forces the CUDA-core predictor (debugging / cross-checking); default is tcgen05.
 static bool use_simt() {
@@ -163,20 +164,32 @@ using namespace mpvp;
 extern "C" int mpvp_nnedi3_launch(const mpvp_weights* nn, int direction, const float* in, float* out, int n, int h,
                                   int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
                                   int64_t out_stride_y, void* stream) {
+  return mpvp_nnedi3_launch_io(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
+                               nullptr, stream);
+}
+
+extern "C" int mpvp_nnedi3_launch_io(const mpvp_weights* nn, int direction, const void* in, void* out, int n, int h,
+                                     int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                                     int64_t out_stride_y, const mpvp_io* io, void* stream) {
+  IoFmt iof;
+  if (int rc0 = parse_io(io, iof)) return rc0;
   MPVP_REQUIRE(nn && nn->kind == 1 && nn->nn_w && nn->nn_bias, "nn handle is null or not an NNEDI3 weight set");
   MPVP_REQUIRE(direction == 0 || direction == 1, "direction %d", direction);
   MPVP_REQUIRE(in && out, "null frame pointer");
   MPVP_REQUIRE(n >= 0 && h >= 1 && w >= 1, "bad frame geometry n=%d h=%d w=%d", n, h, w);
   if (direction == 1)
-    MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) == 0,
-                 "double_x output rows must be 8-byte aligned (even strides)");
+    MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) % (2 * fmt_bytes(iof.out_fmt))) == 0,
+                 "double_x output rows must be aligned to a pixel pair (even strides, base aligned to two elements)");
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(nn->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", nn->device);
-  if (use_simt())
-    return nnedi3_simt(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
-                       static_cast<cudaStream_t>(stream));
+  if (use_simt()) {
+    MPVP_REQUIRE(iof.in_fmt == MPVP_FMT_F32 && iof.out_fmt == MPVP_FMT_F32, "the CUDA-core cross-check path is float32 only");
+    return nnedi3_simt(nn, direction, static_cast<const float*>(in), static_cast<float*>(out), n, h, w, in_stride_n,
+                       in_stride_y, out_stride_n, out_stride_y, static_cast<cudaStream_t>(stream));
+  }
   MPVP_REQUIRE(nn->nn_b, "NNEDI3 weight set has no packed tensor-core operand");
-  return nnedi3_tc(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y,
+  return nnedi3_tc(nn, direction, in, out, n, h, w, in_stride_n, in_stride_y, out_stride_n, out_stride_y, iof,
                    static_cast<cudaStream_t>(stream));
 }

@@ -29,8 +29,9 @@ namespace mpvp {
 namespace {
 
 struct NnTcArgs {
-  const float* __restrict__ in;
-  float* __restrict__ out;
+  const void* __restrict__ in;   // planes of format io.in_fmt
+  void* __restrict__ out;        // planes of format io.out_fmt
+  IoFmt io;
   const void* __restrict__ b_packed;  // [K/8][N][8] binary16
   const float* __restrict__ bias;     // [N] interleaved (b1*log2e, b2)
   int n, h, w;
@@ -240,13 +241,18 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int x0 = tix * kTileW, y0 = tiy * kTileH;
-    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+    const int64_t src0 = (int64_t)f * A.in_sn;
     for (int i = lt; i < SW * SH; i += 128) {
       const int sy = i / SW, sx = i - sy * SW;
       const int gx = clampi(x0 + sx - OX, 0, A.w - 1), gy = clampi(y0 + sy - OY, 0, A.h - 1);
-      const uint32_t dst = smem_u32(my_stage + i);
-      const float* g = src + (int64_t)gy * A.in_sy + gx;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
+      const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+      if (A.io.in_fmt == MPVP_FMT_F32) {
+        const uint32_t dst = smem_u32(my_stage + i);
+        const float* g = static_cast<const float*>(A.in) + off;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
+      } else {  // other plane formats are converted on the way in (synchronous loads)
+        my_stage[i] = load_px(A.in, off, A.io.in_fmt, A.io.in_max);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -407,12 +413,12 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     const int x = x0 + tx, y = y0 + ty;
     if (x < A.w && y < A.h) {
       const float pred = fminf(fmaxf(mstd0 + 5.0f * vsum / wsum * mstd1, 0.f), 1.f);
-      float* __restrict__ o = A.out + (int64_t)f * A.out_sn;
+      const int64_t o = (int64_t)f * A.out_sn;
       if (DIR == 0) {
-        __stcs(o + (int64_t)(2 * y) * A.out_sy + x, orig);
-        __stcs(o + (int64_t)(2 * y + 1) * A.out_sy + x, pred);
+        store_px(A.out, o + (int64_t)(2 * y) * A.out_sy + x, orig, A.io.out_fmt, A.io.out_max);
+        store_px(A.out, o + (int64_t)(2 * y + 1) * A.out_sy + x, pred, A.io.out_fmt, A.io.out_max);
       } else {
-        __stcs(reinterpret_cast<float2*>(o + (int64_t)y * A.out_sy + 2 * x), make_float2(orig, pred));
+        store_px2(A.out, o + (int64_t)y * A.out_sy + 2 * x, orig, pred, A.io.out_fmt, A.io.out_max);
       }
     }
   }
@@ -531,13 +537,18 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_pipe_kernel(const __gri
     if (i < n_my) {
       int x0, y0, f;
       tile_xyf(i, x0, y0, f);
-      const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+      const int64_t src0 = (int64_t)f * A.in_sn;
       for (int e = tx; e < SWP * HY; e += 32) {
         const int sy = e / SWP, sx = e - sy * SWP;
         const int gx = clampi(x0 + sx - OX, 0, A.w - 1), gy = clampi(y0 + ty + sy - OY, 0, A.h - 1);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(my_stage + e)),
-                     "l"(src + (int64_t)gy * A.in_sy + gx)
-                     : "memory");
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        if (A.io.in_fmt == MPVP_FMT_F32) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(my_stage + e)),
+                       "l"(static_cast<const float*>(A.in) + off)
+                       : "memory");
+        } else {
+          my_stage[e] = load_px(A.in, off, A.io.in_fmt, A.io.in_max);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -693,12 +704,12 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_pipe_kernel(const __gri
       if (x < A.w && y < A.h) {
         const float wsum = wsum2.x + wsum2.y, vsum = -(vsum2.x + vsum2.y);
         const float pred = fminf(fmaxf(m0c + 5.0f * vsum / wsum * m1c, 0.f), 1.f);
-        float* __restrict__ o = A.out + (int64_t)f * A.out_sn;
+        const int64_t o = (int64_t)f * A.out_sn;
         if (DIR == 0) {
-          __stcs(o + (int64_t)(2 * y) * A.out_sy + x, origc);
-          __stcs(o + (int64_t)(2 * y + 1) * A.out_sy + x, pred);
+          store_px(A.out, o + (int64_t)(2 * y) * A.out_sy + x, origc, A.io.out_fmt, A.io.out_max);
+          store_px(A.out, o + (int64_t)(2 * y + 1) * A.out_sy + x, pred, A.io.out_fmt, A.io.out_max);
         } else {
-          __stcs(reinterpret_cast<float2*>(o + (int64_t)y * A.out_sy + 2 * x), make_float2(origc, pred));
+          store_px2(A.out, o + (int64_t)y * A.out_sy + 2 * x, origc, pred, A.io.out_fmt, A.io.out_max);
         }
       }
       m0c = m0n; m1c = m1n; origc = orign;
@@ -814,9 +825,11 @@ int dispatch_nns(const NnTcArgs& a, int nns, int device, cudaStream_t st) {
 // B row order the kernels expect for a given nns: the pipelined kernel (nns >= 128) stages 16 columns at a time
 int nnedi3_group_size(int nns) { return (nns >= 128 && pipe_enabled()) ? 8 : 16; }
 
-int nnedi3_tc(const mpvp_weights* nn, int direction, const float* in, float* out, int n, int h, int w,
-              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, cudaStream_t st) {
+int nnedi3_tc(const mpvp_weights* nn, int direction, const void* in, void* out, int n, int h, int w,
+              int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, const IoFmt& io,
+              cudaStream_t st) {
   NnTcArgs a{};
+  a.io = io;
   a.in = in; a.out = out; a.b_packed = nn->nn_b; a.bias = nn->nn_bias; a.group = nn->nn_group;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;

@@ -21,8 +21,9 @@ namespace mpvp {
 namespace {
 
 struct RavuArgs {
-  const float* __restrict__ in;
-  float* __restrict__ out;
+  const void* __restrict__ in;   // planes of format io.in_fmt
+  void* __restrict__ out;        // planes of format io.out_fmt
+  IoFmt io;
   const float4* __restrict__ lut;  // [648][LW]
   const uint2* __restrict__ lut_half;  // same texels as 4 x binary16 (null if the LUT was not rounded to fp16)
   int32_t* __restrict__ bucket;    // [n][3][h][w] or null
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int x0 = tix * kTW, y0 = tiy * kTH;
-    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+    const int64_t src0 = (int64_t)f * A.in_sn;
 
     __syncthreads();
     // ---- stage HOOKED (clamp-to-edge) ---------------------------------------------------
@@ -126,9 +127,11 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const int gy = clampi(y0 + sy - HH, 0, A.h - 1);
       const int64_t off = (int64_t)gy * A.in_sy + gx;
       if (C == 1) {
-        s_h[i] = __ldg(src + off);
+        s_h[i] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
       } else {
-        const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
+        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
+        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
+        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
         s_h[i] = c0;
         s_h[HHt * HW_ + i] = c1;
         s_h[2 * HHt * HW_ + i] = c2;
@@ -187,10 +190,10 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        float* __restrict__ o = A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(2 * y) * A.out_sy + 2 * x;
+        const int64_t o = (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(2 * y) * A.out_sy + 2 * x;
         // (2x,2y)=HOOKED (2x+1,2y)=int10 (2x,2y+1)=int01 (2x+1,2y+1)=int11   (ravu-r2.hook:327-338)
-        __stcs(reinterpret_cast<float2*>(o), make_float2(hb[c * HHt * HW_], r10[c]));
-        __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(r01[c], ib[c * IH * IW]));
+        store_px2(A.out, o, hb[c * HHt * HW_], r10[c], A.io.out_fmt, A.io.out_max);
+        store_px2(A.out, o + A.out_sy, r01[c], ib[c * IH * IW], A.io.out_fmt, A.io.out_max);
       }
     }
   }
@@ -243,6 +246,17 @@ extern "C" int mpvp_ravu_launch(const mpvp_weights* lut, const mpvp_key_params* 
                                 const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
                                 int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
                                 int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  return mpvp_ravu_launch_io(lut, key, radius, key_mode, in, out, n, h, w, in_stride_n, in_stride_c, in_stride_y,
+                             out_stride_n, out_stride_c, out_stride_y, bucket_out, nullptr, stream);
+}
+
+extern "C" int mpvp_ravu_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                                   const void* in, void* out, int n, int h, int w, int64_t in_stride_n,
+                                   int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                                   int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io,
+                                   void* stream) {
+  IoFmt iof;
+  if (int rc0 = parse_io(io, iof)) return rc0;
   MPVP_REQUIRE(lut && lut->kind == 0 && lut->lut, "lut handle is null or not a LUT");
   MPVP_REQUIRE(key && in && out, "null argument");
   MPVP_REQUIRE(radius >= 2 && radius <= 4, "radius %d not in {2,3,4}", radius);
@@ -254,12 +268,13 @@ extern "C" int mpvp_ravu_launch(const mpvp_weights* lut, const mpvp_key_params* 
   MPVP_REQUIRE(key->n_gauss == g * g && key->n_strength == 9 && key->n_strength_thr == 0,
                "key params do not describe a RAVU (log2-strength) hook");
   MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (out_stride_c % 2) == 0 &&
-                   (reinterpret_cast<uintptr_t>(out) % 8) == 0,
-               "output rows must be 8-byte aligned (even strides)");
+                   (reinterpret_cast<uintptr_t>(out) % (2 * fmt_bytes(iof.out_fmt))) == 0,
+               "output rows must be aligned to a pixel pair (even strides, base aligned to two elements)");
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   RavuArgs a{};
+  a.io = iof;
   a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;

@@ -27,8 +27,9 @@ namespace mpvp {
 namespace {
 
 struct LiteArgs {
-  const float* __restrict__ in;
-  float* __restrict__ out;
+  const void* __restrict__ in;   // planes of format io.in_fmt
+  void* __restrict__ out;        // planes of format io.out_fmt
+  IoFmt io;
   const float4* __restrict__ lut;  // [rows][LW]
   const uint2* __restrict__ lut_half;  // same texels as 4 x binary16 (present when the LUT was rounded to fp16)
   int32_t* __restrict__ bucket;
@@ -188,7 +189,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int x0 = tix * kTW, y0 = tiy * TH;
-    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+    const int64_t src0 = (int64_t)f * A.in_sn;   // element offset of this frame
     float* __restrict__ s_tile = s_tiles + (TMA ? (it & 1) * TBUF : 0);
 
     if constexpr (TMA) {
@@ -220,9 +221,11 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       const int gy = clampi(y0 + sy - O, 0, A.h - 1);
       const int64_t off = (int64_t)gy * A.in_sy + gx;
       if constexpr (C == 1) {
-        s_tile[i] = __ldg(src + off);
+        s_tile[i] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
       } else {
-        const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
+        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
+        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
+        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
         s_tile[i] = (KEYMODE == 2) ? rgb_luma709(c0, c1, c2) : c0;
         s_tile[PLANE + i] = c0;
         s_tile[2 * PLANE + i] = c1;
@@ -349,10 +352,10 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
             for (int c = 0; c < 4; ++c) res[c] = fminf(fmaxf(res[c], 0.f), 1.f);
           }
           // phase c -> (2x + c/2, 2y + c%2)
-          float* __restrict__ o = A.out + (int64_t)f * A.out_sn + (int64_t)(2 * y) * A.out_sy + 2 * x;
+          const int64_t o = (int64_t)f * A.out_sn + (int64_t)(2 * y) * A.out_sy + 2 * x;
           if (live) {
-            __stcs(reinterpret_cast<float2*>(o), make_float2(res[0], res[2]));
-            __stcs(reinterpret_cast<float2*>(o + A.out_sy), make_float2(res[1], res[3]));
+            store_px2(A.out, o, res[0], res[2], A.io.out_fmt, A.io.out_max);
+            store_px2(A.out, o + A.out_sy, res[1], res[3], A.io.out_fmt, A.io.out_max);
           }
         } else {
           // RAVU-3x: two texels per tap, res0 -> phases 0..3, res1 -> phases 5..8, centre copied
@@ -378,13 +381,12 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
             }
             const float v[9] = {a01.x + ar10.y, a01.y + ar10.x, a23.x + ar32.y, a23.y + ar32.x, -1.f,
                                 b01.x + br10.y, b01.y + br10.x, b23.x + br32.y, b23.y + br32.x};
-            float* __restrict__ o =
-                A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(3 * y) * A.out_sy + 3 * x;
+            const int64_t o = (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(3 * y) * A.out_sy + 3 * x;
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
               const int i = q / 3, j = q % 3;  // imageStore(gid*3 + ivec2(i, j)): x offset i, y offset j
               const float val = (q == 4) ? Cn(O, O) : fminf(fmaxf(v[q], 0.f), 1.f);
-              if (live) __stcs(o + (int64_t)j * A.out_sy + i, val);
+              if (live) store_px(A.out, o + (int64_t)j * A.out_sy + i, val, A.io.out_fmt, A.io.out_max);
             }
           }
         }
@@ -453,7 +455,10 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   bool use_tma = false;
-  if constexpr (C == 1) use_tma = make_plane_tmap(&tmap, a.in, a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
+  if constexpr (C == 1) {  // TMA staging moves float32 texels; other plane formats are converted while staging
+    if (a.io.in_fmt == MPVP_FMT_F32)
+      use_tma = make_plane_tmap(&tmap, static_cast<const float*>(a.in), a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
+  }
   constexpr int AO = Gm::O < 2 ? Gm::O : 2;
   constexpr size_t kPow = AR ? sizeof(float4) * (kTW + 2 * AO) * (TH + 2 * AO) : 0;  // anti-ringing power tile
   const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LW) + 127) & ~(size_t)127) + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4)) + kPow;
@@ -526,17 +531,29 @@ extern "C" int mpvp_ravu_lite_launch(const mpvp_weights* lut, const mpvp_key_par
                                      float ar_strength, const float* in, float* out, int n, int h, int w,
                                      int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
                                      int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  return mpvp_ravu_lite_launch_io(lut, key, radius, ar, ar_strength, in, out, n, h, w, in_stride_n, in_stride_y,
+                                  out_stride_n, out_stride_y, bucket_out, nullptr, stream);
+}
+
+extern "C" int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
+                                        float ar_strength, const void* in, void* out, int n, int h, int w,
+                                        int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
+                                        int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io, void* stream) {
+  IoFmt iof;
+  if (int rc0 = parse_io(io, iof)) return rc0;
   const int taps = (2 * radius - 1) * (2 * radius - 1);
   const int g = radius == 4 ? 5 : 3;
   int rc = check_common(lut, key, radius, in, out, n, h, w, (taps + 1) / 2, 288, g * g);
   if (rc) return rc;
   MPVP_REQUIRE(key->n_strength == 4 && key->n_strength_thr == 3, "ravu-lite expects 3 strength thresholds");
-  MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) == 0,
-               "output rows must be 8-byte aligned (even strides)");
+  MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) % (2 * fmt_bytes(iof.out_fmt))) == 0,
+               "output rows must be aligned to a pixel pair (even strides, base aligned to two elements)");
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   LiteArgs a{};
+  a.io = iof;
   a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sy = in_stride_y; a.out_sn = out_stride_n; a.out_sy = out_stride_y;
@@ -559,6 +576,17 @@ extern "C" int mpvp_ravu3x_launch(const mpvp_weights* lut, const mpvp_key_params
                                   const float* in, float* out, int n, int h, int w, int64_t in_stride_n,
                                   int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
                                   int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  return mpvp_ravu3x_launch_io(lut, key, radius, key_mode, in, out, n, h, w, in_stride_n, in_stride_c, in_stride_y,
+                               out_stride_n, out_stride_c, out_stride_y, bucket_out, nullptr, stream);
+}
+
+extern "C" int mpvp_ravu3x_launch_io(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                                     const void* in, void* out, int n, int h, int w, int64_t in_stride_n,
+                                     int64_t in_stride_c, int64_t in_stride_y, int64_t out_stride_n,
+                                     int64_t out_stride_c, int64_t out_stride_y, int32_t* bucket_out,
+                                     const mpvp_io* io, void* stream) {
+  IoFmt iof;
+  if (int rc0 = parse_io(io, iof)) return rc0;
   const int taps = (2 * radius - 1) * (2 * radius - 1);
   const int g = radius == 4 ? 5 : 3;
   int rc = check_common(lut, key, radius, in, out, n, h, w, taps + 1, 216, g * g);
@@ -569,6 +597,7 @@ extern "C" int mpvp_ravu3x_launch(const mpvp_weights* lut, const mpvp_key_params
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   LiteArgs a{};
+  a.io = iof;
   a.in = in; a.out = out; a.lut = reinterpret_cast<const float4*>(lut->lut); a.lut_half = reinterpret_cast<const uint2*>(lut->lut_half); a.bucket = bucket_out;
   a.n = n; a.h = h; a.w = w;
   a.in_sn = in_stride_n; a.in_sc = in_stride_c; a.in_sy = in_stride_y;

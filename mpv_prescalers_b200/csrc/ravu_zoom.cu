@@ -19,8 +19,9 @@ namespace mpvp {
 namespace {
 
 struct ZoomArgs {
-  const float* __restrict__ in;
-  float* __restrict__ out;
+  const void* __restrict__ in;   // planes of format io.in_fmt
+  void* __restrict__ out;        // planes of format io.out_fmt
+  IoFmt io;
   const void* __restrict__ lut;     // float4 texels, or 4 x binary16 texels (LUTH)
   const void* __restrict__ lut_ar;
   cudaTextureObject_t tex, tex_ar;  // the same LUTs behind LINEAR-filtering texture objects (TEXF kernels)
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
     const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
     const int ox0 = tix * kTOW, oy0 = tiy * kTOH;
-    const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
+    const int64_t src0 = (int64_t)f * A.in_sn;
 
     int bx_first, by_first, bx_last, by_last;
     float dummy;
@@ -146,9 +147,11 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
       const int64_t off = (int64_t)gy * A.in_sy + gx;
       const int d = sy * SWt + sx;
       if constexpr (C == 1) {
-        s_src[d] = __ldg(src + off);
+        s_src[d] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
       } else {
-        const float c0 = __ldg(src + off), c1 = __ldg(src + A.in_sc + off), c2 = __ldg(src + 2 * A.in_sc + off);
+        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
+        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
+        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
         s_src[d] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
         s_src[PLANE + d] = c0;
         s_src[2 * PLANE + d] = c1;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
         } else {
           r = fminf(fmaxf(r, 0.f), 1.f);
         }
-        __stcs(A.out + (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r);
+        store_px(A.out, (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r, A.io.out_fmt, A.io.out_max);
       }
     }
   }
@@ -305,6 +308,18 @@ extern "C" int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights
                                      int h, int w, int out_h, int out_w, int64_t in_stride_n, int64_t in_stride_c,
                                      int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
                                      int64_t out_stride_y, int32_t* bucket_out, void* stream) {
+  return mpvp_ravu_zoom_launch_io(lut, lut_ar, key, radius, key_mode, ar_strength, in, out, n, h, w, out_h, out_w,
+                                  in_stride_n, in_stride_c, in_stride_y, out_stride_n, out_stride_c, out_stride_y,
+                                  bucket_out, nullptr, stream);
+}
+
+extern "C" int mpvp_ravu_zoom_launch_io(const mpvp_weights* lut, const mpvp_weights* lut_ar, const mpvp_key_params* key,
+                                        int radius, int key_mode, float ar_strength, const void* in, void* out, int n,
+                                        int h, int w, int out_h, int out_w, int64_t in_stride_n, int64_t in_stride_c,
+                                        int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_c,
+                                        int64_t out_stride_y, int32_t* bucket_out, const mpvp_io* io, void* stream) {
+  IoFmt iof;
+  if (int rc0 = parse_io(io, iof)) return rc0;
   MPVP_REQUIRE(lut && lut->kind == 0 && lut->lut, "lut handle is null or not a LUT");
   MPVP_REQUIRE(!lut_ar || (lut_ar->kind == 0 && lut_ar->lut && lut_ar->device == lut->device), "bad lut_ar handle");
   MPVP_REQUIRE(key && in && out, "null argument");
@@ -322,6 +337,7 @@ extern "C" int mpvp_ravu_zoom_launch(const mpvp_weights* lut, const mpvp_weights
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
   ZoomArgs a{};
+  a.io = iof;
   a.in = in; a.out = out; a.bucket = bucket_out;
   // binary16 texels are exact whenever the LUT was created with round_to_fp16 (the rgba16f policy)
   const bool half_lut = lut->lut_half && (!lut_ar || lut_ar->lut_half);

@@ -54,7 +54,7 @@ def sum_over_ranks(value: float, device: Optional[torch.device] = None) -> float
     return float(t.item())
 
 
-def prescale_sharded(frames: torch.Tensor, hook, output_size, devices: Sequence, lut_precision: str, is_yuv: bool):
+def prescale_sharded(frames: torch.Tensor, hook, output_size, devices: Sequence, lut_precision: str, is_yuv: bool, **io_kwargs):
     """Split the batch dimension over ``devices``; returns one output tensor per device (None for empty shards)."""
     from .api import prescale
 
@@ -71,5 +71,5 @@ def prescale_sharded(frames: torch.Tensor, hook, output_size, devices: Sequence,
         if part.device != dev:
             part = part.to(dev, non_blocking=True)
         with torch.cuda.device(dev):
-            outs.append(prescale(part, hook, output_size, None, lut_precision, False, is_yuv))
+            outs.append(prescale(part, hook, output_size, None, lut_precision, False, is_yuv, **io_kwargs))
     return outs

@@ -63,3 +63,31 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_plane_io_descriptor_rules():
+    """PlaneIO (the Python face of mpvp_io): default output dtype follows the input, depths are validated."""
+    import pytest
+    import torch
+
+    from mpv_prescalers_b200 import _native
+    from mpv_prescalers_b200.api import PlaneIO
+
+    io = PlaneIO()
+    assert io.is_default and io.desc().in_format == _native.FMT_F32 and io.desc().out_format == _native.FMT_F32
+    io = PlaneIO(torch.uint8)
+    assert io.out_dtype == torch.uint8 and io.in_max == 255.0 and io.out_max == 255.0
+    io = PlaneIO(torch.uint16, bit_depth=10)
+    assert io.in_max == 1023.0 and io.out_max == 1023.0 and io.desc().in_format == _native.FMT_U16
+    io = PlaneIO(torch.uint16, torch.uint8, bit_depth=10)
+    assert io.out_max == 255.0                      # a 10-bit depth does not fit uint8: full 8-bit range
+    io = PlaneIO(torch.uint8, torch.float16)
+    d = io.desc()
+    assert (d.in_format, d.out_format) == (_native.FMT_U8, _native.FMT_F16)
+    # chains: only the first launch reads the integer plane, only the last one writes the output format
+    mid = io.desc(first=True, last=False)
+    assert (mid.in_format, mid.out_format) == (_native.FMT_U8, _native.FMT_F32)
+    with pytest.raises(ValueError):
+        PlaneIO(torch.uint8, bit_depth=10)
+    with pytest.raises(TypeError):
+        PlaneIO(torch.int32)

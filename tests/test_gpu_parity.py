@@ -41,17 +41,32 @@ def _dilate(mask_bad, r):
     return binary_dilation(mask_bad, structure=np.ones((2 * r + 1, 2 * r + 1), bool))
 
 
-def _run_ravu_variant(name, n, h, w, config, out_hw=None):
+def _quantise_planes(x, bits):
+    """float planes -> (raw integer planes, the float32 planes the shader sees: raw / (2**bits - 1))."""
+    mx = np.float32((1 << bits) - 1)
+    raw = np.rint(np.clip(x, 0, 1) * mx).astype(np.uint8 if bits <= 8 else np.uint16)
+    return raw, (raw.astype(np.float32) / mx).astype(np.float32)
+
+
+def _run_ravu_variant(name, n, h, w, config, out_hw=None, in_bits=None):
+    """in_bits: feed the kernel UNORM integer planes of that depth (uint8 / uint16) and ask for float32 output; the
+    oracle runs on raw / (2**bits - 1), which is what HOOKED_tex() returns for such a plane."""
     from mpv_prescalers_b200 import HookFile, prescale
 
     _need_gpu()
     hk = HookFile.parse(hook_path(name))
     v = hk.variant
     x = _frames(v, n, h, w, config)
-    xt = torch.from_numpy(x).cuda()
+    kw = {}
+    if in_bits is None:
+        xt = torch.from_numpy(x).cuda()
+    else:
+        raw, x = _quantise_planes(x, in_bits)
+        xt = torch.from_numpy(raw).cuda()
+        kw = dict(out_dtype=torch.float32, bit_depth=in_bits)
     if v.channels == 1:
         xt = xt[:, 0]
-    out, bk = prescale(xt, hk, output_size=out_hw, return_buckets=True)
+    out, bk = prescale(xt, hk, output_size=out_hw, return_buckets=True, **kw)
     torch.cuda.synchronize()
     out = out.cpu().numpy()
     bk = bk.cpu().numpy()
@@ -175,6 +190,81 @@ def test_nnedi3_single_axis_when():
     assert tuple(out.shape) == (1, 1, 80, 64) and out.offset == (0.0, -0.5)
     ref, _ = nnedi3_np.nnedi3(x[0, 0], hk.variant, double_y=True, double_x=False)
     check_output(out.cpu().numpy()[0, 0], ref, None, "double_y only")
+
+
+# ---- plane formats (integer video planes in, integer / half planes out) ----------
+
+IO_HOOKS = ["ravu-lite-ar-r3.hook", "ravu-r3.hook", "ravu-r2-rgb.hook", "compute/ravu-3x-r2.hook", "ravu-zoom-r2.hook"]
+
+
+@pytest.mark.parametrize("bits", [8, 10, 16])
+@pytest.mark.parametrize("name", IO_HOOKS)
+def test_integer_input_planes_match_oracle(name, bits):
+    """uint8 / 10-bit-in-uint16 / uint16 planes in: same bucket and output criteria as the float32 path, against the
+    oracle evaluated on raw / (2**bits - 1)."""
+    out_hw = (113, 171) if "zoom" in name else None
+    _run_ravu_variant(name, n=1, h=48, w=70, config=21, out_hw=out_hw, in_bits=bits)
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+def test_integer_input_planes_nnedi3(bits):
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import nnedi3_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("nnedi3-nns32-win8x4.hook"))
+    raw, x = _quantise_planes(batch(1, 1, 50, 90, config=22), bits)
+    out = prescale(torch.from_numpy(raw).cuda(), hk, out_dtype=torch.float32, bit_depth=bits)
+    ref, _ = nnedi3_np.nnedi3(x[0, 0], hk.variant)
+    check_output(out.cpu().numpy()[0, 0], ref, None, f"nnedi3 u{bits} in")
+
+
+@pytest.mark.parametrize("name", IO_HOOKS + ["nnedi3-nns32-win8x4.hook", "nnedi3-nns128-win8x4.hook"])
+def test_output_plane_formats_are_exact_stores(name):
+    """Integer / half OUTPUT planes must be exactly the float32 result pushed through the store rule
+    rint(clamp(v, 0, 1) * (2**bits - 1)) resp. round-to-nearest-even binary16: the arithmetic is the same kernel."""
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    v = hk.variant
+    raw, _ = _quantise_planes(_frames(v, 2, 40, 66, 23), 8)
+    xt = torch.from_numpy(raw).cuda()
+    if v.channels == 1:
+        xt = xt[:, 0]
+    out_hw = (93, 150) if v.family == "ravu-zoom" else None
+    ref = prescale(xt, hk, output_size=out_hw, out_dtype=torch.float32)
+    for dt, bits in ((torch.uint8, 8), (torch.uint16, 10), (torch.uint16, 16), (torch.float16, None)):
+        got = prescale(xt, hk, output_size=out_hw, out_dtype=dt, out_bit_depth=bits)
+        assert got.dtype == dt and got.shape == ref.shape
+        if bits is None:
+            want = ref.to(torch.float16)
+            assert torch.equal(got.view(torch.int16), want.view(torch.int16)), f"{name}: float16 store differs"
+        else:
+            mx = float((1 << bits) - 1)
+            want = torch.round(ref.clamp(0, 1) * mx)           # torch.round is round-half-even
+            diff = (got.to(torch.float32) - want).abs().max().item()
+            assert diff == 0, f"{name}: {dt} / {bits}-bit store differs from the float32 result by {diff} LSB"
+    # the default output dtype follows the input dtype (uint8 in -> uint8 out, same depth)
+    same = prescale(xt, hk, output_size=out_hw)
+    assert same.dtype == torch.uint8
+
+
+def test_integer_planes_host_tensors_and_strided_views():
+    """CPU uint8 tensors are staged through the GPU like float32 ones; channel-sliced device views run in place."""
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path("ravu-lite-r3.hook"))
+    raw, _ = _quantise_planes(_frames(hk.variant, 3, 30, 52, 24), 8)
+    xd = torch.from_numpy(raw).cuda()[:, 0]
+    dev = prescale(xd, hk)
+    host = prescale(torch.from_numpy(raw)[:, 0], hk)
+    assert host.device.type == "cpu" and host.dtype == torch.uint8 and torch.equal(host, dev.cpu())
+    packed = torch.zeros((3, 2, 30, 52), dtype=torch.uint8, device="cuda")
+    packed[:, 1] = xd
+    assert torch.equal(prescale(packed[:, 1], hk), dev)
 
 
 # ---- edge cases ---------------------------------------------------------------------------------
