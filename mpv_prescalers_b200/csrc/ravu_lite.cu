@@ -114,7 +114,9 @@ __device__ __forceinline__ bool elect_one() {
 // LH: LUT kept in shared memory as 4 x binary16 per texel (exact: the texels ARE binary16 values, App. D.1).  A warp's
 // 32 lanes gather 32 different LUT rows, so the gather is bank-conflict bound: 8-byte texels need half the
 // shared-memory wavefronts of 16-byte ones (68 vs 133 per 13-texel row on the config-2 planes).
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH>
+// OF32: the output planes are float32 at compile time (the runtime format switch at the store costs 2.8 % on the
+// register-bound -ar kernel: 3.53 vs 3.43 ms); false = any mpvp_io output format.
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH, bool OF32>
 __global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
@@ -354,8 +356,9 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
           // phase c -> (2x + c/2, 2y + c%2)
           const int64_t o = (int64_t)f * A.out_sn + (int64_t)(2 * y) * A.out_sy + 2 * x;
           if (live) {
-            store_px2(A.out, o, res[0], res[2], A.io.out_fmt, A.io.out_max);
-            store_px2(A.out, o + A.out_sy, res[1], res[3], A.io.out_fmt, A.io.out_max);
+            const int ofmt = OF32 ? MPVP_FMT_F32 : A.io.out_fmt;
+            store_px2(A.out, o, res[0], res[2], ofmt, A.io.out_max);
+            store_px2(A.out, o + A.out_sy, res[1], res[3], ofmt, A.io.out_max);
           }
         } else {
           // RAVU-3x: two texels per tap, res0 -> phases 0..3, res1 -> phases 5..8, centre copied
@@ -386,7 +389,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
             for (int q = 0; q < 9; ++q) {
               const int i = q / 3, j = q % 3;  // imageStore(gid*3 + ivec2(i, j)): x offset i, y offset j
               const float val = (q == 4) ? Cn(O, O) : fminf(fmaxf(v[q], 0.f), 1.f);
-              if (live) store_px(A.out, o + (int64_t)j * A.out_sy + i, val, A.io.out_fmt, A.io.out_max);
+              if (live) store_px(A.out, o + (int64_t)j * A.out_sy + i, val, OF32 ? MPVP_FMT_F32 : A.io.out_fmt, A.io.out_max);
             }
           }
         }
@@ -439,7 +442,7 @@ bool make_plane_tmap(CUtensorMap* tm, const float* base, int w, int h, int n, in
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool LH>
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool LH, bool OF32>
 int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   using Gm = LiteGeom<R>;
   constexpr int LW = ((SCALE == 2) ? (Gm::TAPS + 1) / 2 : (Gm::TAPS + 1)) | 1;  // padded pitch
@@ -462,9 +465,9 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   constexpr int AO = Gm::O < 2 ? Gm::O : 2;
   constexpr size_t kPow = AR ? sizeof(float4) * (kTW + 2 * AO) * (TH + 2 * AO) : 0;  // anti-ringing power tile
   const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LW) + 127) & ~(size_t)127) + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4)) + kPow;
-  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false, LH>;
+  auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false, LH, OF32>;
   if constexpr (C == 1) {
-    if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH>;
+    if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH, OF32>;
   }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -503,9 +506,12 @@ bool half_lut_enabled() {
 
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C = 1, int KEYMODE = 0>
 int launch_lite(const LiteArgs& a, int device, cudaStream_t stream) {
-  if (exact_key()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, false, false>(a, device, stream);
-  if (a.lut_half && half_lut_enabled()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, true>(a, device, stream);
-  return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, false>(a, device, stream);
+  if (exact_key()) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, false, false, false>(a, device, stream);
+  if (a.lut_half && half_lut_enabled()) {
+    if (a.io.out_fmt == MPVP_FMT_F32) return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, true, true>(a, device, stream);
+    return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, true, false>(a, device, stream);
+  }
+  return launch_lite_impl<R, AR, SCALE, P, STRIPS, C, KEYMODE, true, false, false>(a, device, stream);
 }
 
 int check_common(const mpvp_weights* lut, const mpvp_key_params* key, int radius, const void* in, const void* out,
