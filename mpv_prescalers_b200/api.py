@@ -392,6 +392,7 @@ def prescale(
     out_dtype: Optional[torch.dtype] = None,
     bit_depth: Optional[int] = None,
     out_bit_depth: Optional[int] = None,
+    split: str = "frames",
 ):
     """Apply one mpv-prescalers hook file to a batch of frames.
 
@@ -404,6 +405,9 @@ def prescale(
                   (it is the size produced); ``None`` = the hook's natural 2x / 3x.
     devices       shard the batch dimension over these GPUs (frames are independent, no collective);
                   returns a list with one output tensor per device (outputs stay on their GPU).
+    split         with ``devices``: 'frames' (default) or 'rows' -- split every frame into row bands with a halo,
+                  one band per listed device, and return the re-assembled result on ``devices[0]`` (for a single
+                  large frame; halo rows travel peer-to-peer over NVLink; bit-identical to the unsplit result).
     lut_precision 'fp16' reproduces the reference's rgba16f LUT storage; 'fp32' keeps the file's floats.
     out           optional destination for CPU inputs: a (pinned) CPU tensor ``[N,C,OH,OW]`` of the output dtype
                   that receives the result, so that a video loop does not re-allocate pinned memory per batch.
@@ -420,8 +424,13 @@ def prescale(
     hk = hook if isinstance(hook, HookFile) else HookFile.parse(find_hook(hook))
     v = hk.variant
     if devices is not None:
-        from .sharding import prescale_sharded
+        from .sharding import prescale_rowsplit, prescale_sharded
 
+        if split == "rows":
+            return prescale_rowsplit(frames, hk, output_size, list(devices), lut_precision, is_yuv,
+                                     out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
+        if split != "frames":
+            raise ValueError("split must be 'frames' or 'rows'")
         return prescale_sharded(frames, hk, output_size, list(devices), lut_precision, is_yuv,
                                 out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
     x, in_shape = _normalise_input(frames, v)

@@ -391,6 +391,31 @@ def test_multi_gpu_sharding_equals_single_gpu():
     assert torch.equal(torch.cat([p.cpu() for p in parts]), single)
 
 
+@pytest.mark.parametrize("name", ["ravu-lite-ar-r3.hook", "ravu-r4.hook", "ravu-r2-rgb.hook", "compute/ravu-3x-r3.hook",
+                                  "nnedi3-nns32-win8x6.hook"])
+def test_row_split_is_bit_identical(name):
+    """Single-frame row split: bands with a halo, seams see real neighbouring rows, clamp-to-edge
+    only at the true borders.  Listing device 0 several times exercises the band logic on one GPU; with more GPUs the
+    bands really travel peer-to-peer."""
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    v = hk.variant
+    x = torch.from_numpy(_frames(v, 1, 101, 77, 29)).cuda(0)
+    if v.channels == 1:
+        x = x[:, 0]
+    whole = prescale(x, hk)
+    ndev = torch.cuda.device_count()
+    devs = [i % ndev for i in range(3)]
+    split = prescale(x, hk, devices=devs, split="rows")
+    assert split.device.index == devs[0] and split.shape == whole.shape and split.offset == whole.offset
+    assert torch.equal(split, whole)
+    # integer planes take the same route
+    raw = torch.round(x.clamp(0, 1) * 255).to(torch.uint8)
+    assert torch.equal(prescale(raw, hk, devices=devs, split="rows"), prescale(raw, hk))
+
+
 def test_c_abi_host_entry_point():
     """mpvp_ravu_lite_host: host pointers in, host pointers out."""
     import ctypes

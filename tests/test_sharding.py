@@ -4,7 +4,7 @@ import os
 import pytest
 import torch
 
-from mpv_prescalers_b200.sharding import max_over_ranks, rank_slice, shard_bounds, sum_over_ranks
+from mpv_prescalers_b200.sharding import ROW_HALO, max_over_ranks, rank_slice, row_bands, shard_bounds, sum_over_ranks
 
 
 def test_shard_bounds_partition():
@@ -56,3 +56,14 @@ def test_gloo_world2_frame_sharding():
         assert t == 2.0 and total == 7.0
         flat = [v for part in gathered for v in part]
         assert flat == [float(4 * i) for i in range(7)]  # contiguous, disjoint, complete
+
+
+def test_row_bands_cover_the_frame_with_halo():
+    for h in (1, 7, 64, 2160):
+        for parts in (1, 2, 3, 8):
+            bands = row_bands(h, parts)
+            own = [(a, b) for a, b, _, _ in bands]
+            assert own[0][0] == 0 and own[-1][1] == h and all(own[i][1] == own[i + 1][0] for i in range(parts - 1))
+            for a, b, s0, s1 in bands:
+                if b > a:
+                    assert s0 == max(a - ROW_HALO, 0) and s1 == min(b + ROW_HALO, h)   # halo, clipped at true borders only
