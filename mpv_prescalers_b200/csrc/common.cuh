@@ -98,9 +98,11 @@ __device__ __forceinline__ float div12_rn(float x) {
 template <int FAMILY, int N, class SF>
 __device__ __forceinline__ float key_diff(int k, SF S) {
   if (FAMILY == STENCIL_RAVU && k - 2 >= 0 && k + 2 <= N - 1) {
-    // (-s[+2] + 8.0*s[+1] - 8.0*s[-1] + s[-2]) / 12.0
-    float t = __fadd_rn(-S(2), __fmul_rn(8.0f, S(1)));
-    t = __fsub_rn(t, __fmul_rn(8.0f, S(-1)));
+    // (-s[+2] + 8.0*s[+1] - 8.0*s[-1] + s[-2]) / 12.0, left to right.  8.0*s is exact in binary floating point, so
+    // fma(8, s[+1], -s[+2]) rounds exactly once, like the shader's add of the exact product, and so does the
+    // second term: two FFMA replace two FMUL + two FADD with bit-identical results.
+    float t = __fmaf_rn(8.0f, S(1), -S(2));
+    t = __fmaf_rn(-8.0f, S(-1), t);
     t = __fadd_rn(t, S(-2));
     return div12_rn(t);
   }
