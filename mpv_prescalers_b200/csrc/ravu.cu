@@ -88,7 +88,8 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* 
 }
 
 // KEYMODE: 0 luma (C=1), 1 yuv (key = channel 0), 2 rgb (key = BT.709 luma)
-template <int R, int C, int KEYMODE, int NT, bool LH>
+// OF32: float32 output planes at compile time (the common case; false = any mpvp_io output format)
+template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32>
 __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
   constexpr int N = 2 * R, TAPS = N * N;
   constexpr int LW = (TAPS / 2 + 3) / 4;
@@ -121,23 +122,26 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
 
     __syncthreads();
     // ---- stage HOOKED (clamp-to-edge) ---------------------------------------------------
-    for (int i = tid; i < HW_ * HHt; i += NT) {
-      const int sy = i / HW_, sx = i - sy * HW_;
-      const int gx = clampi(x0 + sx - HH, 0, A.w - 1);
-      const int gy = clampi(y0 + sy - HH, 0, A.h - 1);
-      const int64_t off = (int64_t)gy * A.in_sy + gx;
-      if (C == 1) {
-        s_h[i] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-      } else {
-        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        s_h[i] = c0;
-        s_h[HHt * HW_ + i] = c1;
-        s_h[2 * HHt * HW_ + i] = c2;
-        if (KEYMODE == 2) s_h[3 * HHt * HW_ + i] = rgb_luma(c0, c1, c2);
+    dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
+      constexpr int FMT = decltype(ftag)::value;
+      for (int i = tid; i < HW_ * HHt; i += NT) {
+        const int sy = i / HW_, sx = i - sy * HW_;
+        const int gx = clampi(x0 + sx - HH, 0, A.w - 1);
+        const int gy = clampi(y0 + sy - HH, 0, A.h - 1);
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        if (C == 1) {
+          s_h[i] = load_px_t<FMT>(A.in, off, A.io.in_max);
+        } else {
+          const float c0 = load_px_t<FMT>(A.in, off, A.io.in_max);
+          const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
+          const float c2 = load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max);
+          s_h[i] = c0;
+          s_h[HHt * HW_ + i] = c1;
+          s_h[2 * HHt * HW_ + i] = c2;
+          if (KEYMODE == 2) s_h[3 * HHt * HW_ + i] = rgb_luma(c0, c1, c2);
+        }
       }
-    }
+    });
     __syncthreads();
 
     // ---- phase A: int11 on the tile + halo ------------------------------------------------
@@ -192,14 +196,15 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       for (int c = 0; c < C; ++c) {
         const int64_t o = (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(2 * y) * A.out_sy + 2 * x;
         // (2x,2y)=HOOKED (2x+1,2y)=int10 (2x,2y+1)=int01 (2x+1,2y+1)=int11   (ravu-r2.hook:327-338)
-        store_px2(A.out, o, hb[c * HHt * HW_], r10[c], A.io.out_fmt, A.io.out_max);
-        store_px2(A.out, o + A.out_sy, r01[c], ib[c * IH * IW], A.io.out_fmt, A.io.out_max);
+        const int ofmt = OF32 ? MPVP_FMT_F32 : A.io.out_fmt;
+        store_px2(A.out, o, hb[c * HHt * HW_], r10[c], ofmt, A.io.out_max);
+        store_px2(A.out, o + A.out_sy, r01[c], ib[c * IH * IW], ofmt, A.io.out_max);
       }
     }
   }
 }
 
-template <int R, int C, int KEYMODE, int NT, bool LH>
+template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32>
 int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   constexpr int N = 2 * R, TAPS = N * N, LW = ((TAPS / 2 + 3) / 4) | 1, HH = 2 * R - 1;  // LW: padded pitch
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
@@ -209,7 +214,7 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + kTH - 1) / kTH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  auto kern = ravu_kernel<R, C, KEYMODE, NT, LH>;
+  auto kern = ravu_kernel<R, C, KEYMODE, NT, LH, OF32>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -233,8 +238,11 @@ int launch_ravu(const RavuArgs& a, int device, cudaStream_t stream) {
     const char* e = getenv("MPVP_LUT_SMEM");
     return !(e && e[0] == 'f' && e[2] == '3');
   }();
-  if (a.lut_half && half_ok) return launch_ravu_impl<R, C, KEYMODE, NT, true>(a, device, stream);
-  return launch_ravu_impl<R, C, KEYMODE, NT, false>(a, device, stream);
+  if (a.lut_half && half_ok) {
+    if (a.io.out_fmt == MPVP_FMT_F32) return launch_ravu_impl<R, C, KEYMODE, NT, true, true>(a, device, stream);
+    return launch_ravu_impl<R, C, KEYMODE, NT, true, false>(a, device, stream);
+  }
+  return launch_ravu_impl<R, C, KEYMODE, NT, false, false>(a, device, stream);
 }
 
 }  // namespace

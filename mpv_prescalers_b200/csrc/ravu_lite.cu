@@ -217,23 +217,26 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       }
     } else {
     __syncthreads();  // previous tile fully consumed
-    for (int i = tid; i < SW * SH; i += kThreads) {
-      const int sy = i / SW, sx = i - sy * SW;
-      const int gx = clampi(x0 + sx - XO, 0, A.w - 1);
-      const int gy = clampi(y0 + sy - O, 0, A.h - 1);
-      const int64_t off = (int64_t)gy * A.in_sy + gx;
-      if constexpr (C == 1) {
-        s_tile[i] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-      } else {
-        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        s_tile[i] = (KEYMODE == 2) ? rgb_luma709(c0, c1, c2) : c0;
-        s_tile[PLANE + i] = c0;
-        s_tile[2 * PLANE + i] = c1;
-        s_tile[3 * PLANE + i] = c2;
+    dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
+      constexpr int FMT = decltype(ftag)::value;
+      for (int i = tid; i < SW * SH; i += kThreads) {
+        const int sy = i / SW, sx = i - sy * SW;
+        const int gx = clampi(x0 + sx - XO, 0, A.w - 1);
+        const int gy = clampi(y0 + sy - O, 0, A.h - 1);
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        if constexpr (C == 1) {
+          s_tile[i] = load_px_t<FMT>(A.in, off, A.io.in_max);
+        } else {
+          const float c0 = load_px_t<FMT>(A.in, off, A.io.in_max);
+          const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
+          const float c2 = load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max);
+          s_tile[i] = (KEYMODE == 2) ? rgb_luma709(c0, c1, c2) : c0;
+          s_tile[PLANE + i] = c0;
+          s_tile[2 * PLANE + i] = c1;
+          s_tile[3 * PLANE + i] = c2;
+        }
       }
-    }
+    });
     __syncthreads();
     }
 

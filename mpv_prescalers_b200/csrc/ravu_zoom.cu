@@ -141,23 +141,26 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     }
     // ---- stage the source rectangle (clamp-to-edge) ------------------------------------------------
     const int need_w = ncx + N - 1, need_h = ncy + N - 1;
-    for (int i = tid; i < need_w * need_h; i += kNT) {
-      const int sy = i / need_w, sx = i - sy * need_w;
-      const int gx = clampi(sx0 + sx, 0, A.w - 1), gy = clampi(sy0 + sy, 0, A.h - 1);
-      const int64_t off = (int64_t)gy * A.in_sy + gx;
-      const int d = sy * SWt + sx;
-      if constexpr (C == 1) {
-        s_src[d] = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-      } else {
-        const float c0 = load_px(A.in, src0 + off, A.io.in_fmt, A.io.in_max);
-        const float c1 = load_px(A.in, src0 + A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        const float c2 = load_px(A.in, src0 + 2 * A.in_sc + off, A.io.in_fmt, A.io.in_max);
-        s_src[d] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
-        s_src[PLANE + d] = c0;
-        s_src[2 * PLANE + d] = c1;
-        s_src[3 * PLANE + d] = c2;
+    dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
+      constexpr int FMT = decltype(ftag)::value;
+      for (int i = tid; i < need_w * need_h; i += kNT) {
+        const int sy = i / need_w, sx = i - sy * need_w;
+        const int gx = clampi(sx0 + sx, 0, A.w - 1), gy = clampi(sy0 + sy, 0, A.h - 1);
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        const int d = sy * SWt + sx;
+        if constexpr (C == 1) {
+          s_src[d] = load_px_t<FMT>(A.in, off, A.io.in_max);
+        } else {
+          const float c0 = load_px_t<FMT>(A.in, off, A.io.in_max);
+          const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
+          const float c2 = load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max);
+          s_src[d] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
+          s_src[PLANE + d] = c0;
+          s_src[2 * PLANE + d] = c1;
+          s_src[3 * PLANE + d] = c2;
+        }
       }
-    }
+    });
     __syncthreads();
     // ---- one key per source cell: every output pixel whose base texel coincides shares window and bucket ----
     for (int i = tid; i < ncx * ncy; i += kNT) {
