@@ -9,18 +9,19 @@ import torch, time, json
 from mpv_prescalers_b200 import prescale
 x = torch.rand(1, 4320, 7680, device="cuda:0")
 res = {}
-for devs in ([0], [0, 1]):
-    run = (lambda: prescale(x, "ravu-lite-ar-r3.hook", devices=devs, split="rows")) if len(devs) > 1 else (lambda: prescale(x, "ravu-lite-ar-r3.hook"))
-    for _ in range(3):
+for hook in ("ravu-lite-ar-r3.hook", "ravu-r4.hook", "nnedi3-nns256-win8x6.hook"):
+  for devs in ([0], [0, 1]):
+    run = (lambda: prescale(x, hook, devices=devs, split="rows")) if len(devs) > 1 else (lambda: prescale(x, hook))
+    for _ in range(2):
         o = run()
     for d in range(torch.cuda.device_count()):
         torch.cuda.synchronize(d)
     t = time.perf_counter()
-    for _ in range(10):
+    for _ in range(5):
         o = run()
     for d in range(torch.cuda.device_count()):
         torch.cuda.synchronize(d)
-    res[str(devs)] = (time.perf_counter() - t) / 10 * 1e3
-    print("8K frame ravu-lite-ar-r3 on", devs, res[str(devs)], "ms")
+    res[hook + " " + str(devs)] = (time.perf_counter() - t) / 5 * 1e3
+    print("8K frame", hook, "on", devs, res[hook + " " + str(devs)], "ms")
 json.dump(res, open("gpurun_out/r01_rowsplit_8k.json", "w"))
 PY
