@@ -45,9 +45,10 @@ __global__ void __launch_bounds__(kNT) nnedi3_simt_kernel(const __grid_constant_
   const int tx = tid % kTW, ty = tid / kTW;
 
   for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const unsigned tq = (unsigned)tile / (unsigned)A.tiles_x;   // total_tiles < 2^31 (checked by the host)
+    const int tix = (int)((unsigned)tile - tq * (unsigned)A.tiles_x);
+    const int f = (int)(tq / (unsigned)A.tiles_y);
+    const int tiy = (int)(tq - (unsigned)f * (unsigned)A.tiles_y);
     const int x0 = tix * kTW, y0 = tiy * kTH;
     const float* __restrict__ src = A.in + (int64_t)f * A.in_sn;
     __syncthreads();
@@ -113,6 +114,7 @@ int launch_simt(const NnArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w_ + kTW - 1) / kTW;
   a.tiles_y = (a.h + kTH - 1) / kTH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   auto kern = nnedi3_simt_kernel<S, DIR>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

@@ -165,6 +165,12 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   constexpr int N = 2 * NNS;                // accumulator columns per pixel
   constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk (64 neurons)
   constexpr int NCH = N / CN;
+  // Small networks (nns16 / nns32: one chunk of <= 64 columns per tile) keep TWO tiles in flight per warpgroup: the A
+  // operand and the MMA of tile t+1 are issued before the epilogue of tile t starts (two A buffers, two TMEM slots,
+  // two mbarriers), so the build -> MMA -> epilogue latency chain of a tile, which dominates when the epilogue is
+  // only 16-32 neurons long, overlaps the neighbouring tile's work.
+  constexpr bool DB = (NCH == 1 && CN <= 64);
+  constexpr int NA = DB ? 2 : 1;            // A buffers per warpgroup
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_b = smem;                               // B operand
   unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
-  float* s_stage = reinterpret_cast<float*>(s_a + kWG * kABytes);  // [kWG][STG]
+  float* s_stage = reinterpret_cast<float*>(s_a + kWG * NA * kABytes);  // [kWG][STG]
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] + 1
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 2 * kWG + 1);
 
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
-  unsigned char* my_a = s_a + wg * kABytes;
+  unsigned char* my_a = s_a + wg * NA * kABytes;
   {
     // constant tail of every A row: the bias step (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8)
     const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
@@ -200,9 +206,11 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     uint4 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
     pk.z = *reinterpret_cast<uint32_t*>(&hz); pk.w = pk.z;
-    *reinterpret_cast<uint4*>(my_a + KC * (128 * 16) + lt * 16) = pk;
+#pragma unroll
+    for (int bufi = 0; bufi < NA; ++bufi) *reinterpret_cast<uint4*>(my_a + bufi * kABytes + KC * (128 * 16) + lt * 16) = pk;
     pk.x = pk.y = pk.z;
-    *reinterpret_cast<uint4*>(my_a + (KC + 1) * (128 * 16) + lt * 16) = pk;
+#pragma unroll
+    for (int bufi = 0; bufi < NA; ++bufi) *reinterpret_cast<uint4*>(my_a + bufi * kABytes + (KC + 1) * (128 * 16) + lt * 16) = pk;
   }
   tc_fence_before();
   __syncthreads();
@@ -222,25 +230,23 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
 
-  auto issue_chunk = [&](int c) {
-    // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T
+  auto issue_chunk = [&](int c, int slot = 0) {
+    // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T   (slot: A buffer / TMEM slot / mbarrier of the DB mode)
 #pragma unroll
     for (int j = 0; j < KX / 16; ++j) {
-      const uint64_t ad = make_desc(a_addr + j * 2 * (128 * 16), 128 * 16, 128);
+      const uint64_t ad = make_desc(a_addr + slot * kABytes + j * 2 * (128 * 16), 128 * 16, 128);
       const uint64_t bd = make_desc(b_addr + c * CN * 16 + j * 2 * (N * 16), N * 16, 128);
-      umma_f16(d_col, ad, bd, idesc, j > 0 ? 1u : 0u);
+      umma_f16(d_col + (uint32_t)(slot * CN), ad, bd, idesc, j > 0 ? 1u : 0u);
     }
-    umma_commit(my_mbar);
+    umma_commit(my_mbar + 8u * (uint32_t)slot);
   };
 
   // asynchronous staging of a tile's source rectangle (clamp-to-edge): cp.async, no registers held, so the
   // loads of tile t+1 fly under the epilogue of tile t
-  auto prefetch_tile = [&](long long tile) {
+  auto prefetch_tile = [&](long long tile, const TileWalk& tw) {
     if (tile >= A.total_tiles) return;
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
-    const int x0 = tix * kTileW, y0 = tiy * kTileH;
+    const int f = tw.f;
+    const int x0 = tw.tix * kTileW, y0 = tw.tiy * kTileH;
     const int64_t src0 = (int64_t)f * A.in_sn;
     for (int i = lt; i < SW * SH; i += 128) {
       const int sy = i / SW, sx = i - sy * SW;
@@ -257,21 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const long long tile_step = (long long)gridDim.x * kWG;
-  prefetch_tile((long long)blockIdx.x * kWG + wg);
-
-  for (long long tile = (long long)blockIdx.x * kWG + wg; tile < A.total_tiles; tile += tile_step) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
-    const int x0 = tix * kTileW, y0 = tiy * kTileH;
-
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    wg_barrier(wg);  // the staged window of this tile is complete and visible
-
-    // ---- im2col + normalisation -> A operand ----------------------------------------------------
-    float mstd0, mstd1, orig;
-    {
+  // im2col + normalisation of the staged window -> A operand in `abuf`; returns the pixel's mean, stddev and centre sample
+  auto build_a = [&](unsigned char* abuf, float& mstd0, float& mstd1, float& orig) {
       float xs[K];
       float sum = 0.f, sumsq = 0.f;
 #pragma unroll
@@ -298,35 +291,66 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
         pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
         pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
         pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-        *reinterpret_cast<uint4*>(my_a + kc * (128 * 16) + lt * 16) = pk;
+        *reinterpret_cast<uint4*>(abuf + kc * (128 * 16) + lt * 16) = pk;
       }
-    }
+  };
+
+  const long long tile_step = (long long)gridDim.x * kWG;
+
+  struct TileCtx {
+    float mstd0, mstd1, orig;
+    int x0, y0, f;
+  };
+  // front half of a tile: staged window -> A operand (buffer `slot`) -> MMA of chunk 0 into TMEM slot `slot`
+  // `ahead` always stands one tile beyond the tile whose front half runs (it is the tile being prefetched)
+  TileWalk ahead((long long)blockIdx.x * kWG + wg, tile_step, A.tiles_x, A.tiles_y);
+  auto front = [&](long long tile, int slot, TileCtx& tc) {
+    tc.f = ahead.f;
+    tc.x0 = ahead.tix * kTileW;
+    tc.y0 = ahead.tiy * kTileH;
+    ahead.next();
+
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    wg_barrier(wg);  // the staged window of this tile is complete and visible
+
+    // ---- im2col + normalisation -> A operand ----------------------------------------------------
+    build_a(my_a + slot * kABytes, tc.mstd0, tc.mstd1, tc.orig);
     fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor core (async proxy)
-    tc_fence_before();     // orders the previous tile's tcgen05.ld before the new MMAs
+    tc_fence_before();     // orders the previous tiles' tcgen05.ld before the new MMAs
     wg_barrier(wg);        // A complete; nobody reads the staging buffer any more
     if (lt == 0) {
       tc_fence_after();
-      issue_chunk(0);
+      issue_chunk(0, slot);
     }
-    prefetch_tile(tile + tile_step);
+    prefetch_tile(tile + tile_step, ahead);
+  };
 
+  // back half: epilogue over the accumulator chunks of the tile (TMEM slot `slot`), then the store
+  auto back = [&](const TileCtx& tc, int slot, uint32_t parity) {
+    const float mstd0 = tc.mstd0, mstd1 = tc.mstd1, orig = tc.orig;
+    const int x0 = tc.x0, y0 = tc.y0, f = tc.f;
+    const uint32_t d_lane_s = d_lane + (uint32_t)(slot * CN);
     // ---- epilogue -----------------------------------------------------------------------------
     float wsum = 0.f, vsum = 0.f;
     float2 wsum2 = make_float2(0.f, 0.f), vsum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
-      mbar_wait(my_mbar, phase);
-      phase ^= 1;
+      if constexpr (DB) {
+        mbar_wait(my_mbar + 8u * (uint32_t)slot, parity);
+      } else {
+        mbar_wait(my_mbar, phase);
+        phase ^= 1;
+      }
       tc_fence_after();
       uint32_t va[32], vb[32];
-      tmem_ld32_issue(d_lane, va);
+      tmem_ld32_issue(d_lane_s, va);
 #pragma unroll
       for (int i = 0; i < CN / 32; ++i) {
         uint32_t (&cur)[32] = (i & 1) ? vb : va;
         uint32_t (&nxt)[32] = (i & 1) ? va : vb;
         tmem_ld_wait();
         if (i + 1 < CN / 32) {
-          tmem_ld32_issue(d_lane + (i + 1) * 32, nxt);
+          tmem_ld32_issue(d_lane_s + (i + 1) * 32, nxt);
         } else if (c + 1 < NCH) {
           // the last columns of this chunk are in registers: the accumulator is free, so the MMA of the
           // next chunk is issued now and runs under the arithmetic of this last block
@@ -420,6 +444,29 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
       } else {
         store_px2(A.out, o + (int64_t)y * A.out_sy + 2 * x, orig, pred, A.io.out_fmt, A.io.out_max);
       }
+    }
+  };
+
+  const long long first = (long long)blockIdx.x * kWG + wg;
+  prefetch_tile(first, ahead);
+  if constexpr (DB) {
+    // two tiles in flight: front(t+1) is issued before back(t)
+    if (first < A.total_tiles) {
+      TileCtx cur, nxt;
+      front(first, 0, cur);
+      uint32_t it = 0;
+      for (long long tile = first; tile < A.total_tiles; tile += tile_step, ++it) {
+        const bool more = tile + tile_step < A.total_tiles;
+        if (more) front(tile + tile_step, (int)((it + 1) & 1), nxt);
+        back(cur, (int)(it & 1), (it >> 1) & 1);
+        if (more) cur = nxt;
+      }
+    }
+  } else {
+    for (long long tile = first; tile < A.total_tiles; tile += tile_step) {
+      TileCtx tc;
+      front(tile, 0, tc);
+      back(tc, 0, 0);
     }
   }
 
@@ -527,10 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_pipe_kernel(const __gri
   const int total_jobs = n_my * NJ;
 
   auto tile_xyf = [&](int i, int& x0, int& y0, int& f) {
-    const long long tile = first + (long long)i * tile_step;
-    x0 = (int)(tile % A.tiles_x) * kTileW;
-    y0 = (int)((tile / A.tiles_x) % A.tiles_y) * kTileH;
-    f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+    const unsigned tile = (unsigned)(first + (long long)i * tile_step);   // total_tiles < 2^31 (checked by the host)
+    const unsigned q = tile / (unsigned)A.tiles_x;
+    x0 = (int)(tile - q * (unsigned)A.tiles_x) * kTileW;
+    const unsigned ff = q / (unsigned)A.tiles_y;
+    y0 = (int)(q - ff * (unsigned)A.tiles_y) * kTileH;
+    f = (int)ff;
   };
   // stage (asynchronously) the window rows this warp's 32 pixels tap, clamp-to-edge
   auto prefetch = [&](int i) {
@@ -759,6 +808,7 @@ int launch_tc_pipe(const NnTcArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w + kTileW - 1) / kTileW;
   a.tiles_y = (a.h + kTileH - 1) / kTileH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   auto kern = nnedi3_tc_pipe_kernel<S, DIR, NNS>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = sm_count(device);
@@ -784,13 +834,15 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
   constexpr int STG = (SW * SH + 3) & ~3;
-  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (2 * kWG + 1) + 16;
+  constexpr int NA = (N <= 64) ? 2 : 1;  // A buffers per warpgroup (two tiles in flight for nns16 / nns32)
+  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * NA * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (2 * kWG + 1) + 16;
   // one CTA per SM: the kernel allocates all 512 TMEM columns
   if (smem < 120 * 1024) smem = 120 * 1024;
   NnTcArgs a = a0;
   a.tiles_x = (a.w + kTileW - 1) / kTileW;
   a.tiles_y = (a.h + kTileH - 1) / kTileH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   const int mode = epi_mode();
   auto kern = mode == 0 ? nnedi3_tc_kernel<S, DIR, NNS, 0>
               : mode == 1 ? nnedi3_tc_kernel<S, DIR, NNS, 1>

@@ -113,10 +113,9 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
     for (int i = tid; i < 648 * LW; i += NT) s_lut[(i / LW) * LWP + (i % LW)] = A.lut[i];
   }
 
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+  TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next()) {
+    const int tix = walk.tix, tiy = walk.tiy, f = walk.f;
     const int x0 = tix * kTW, y0 = tiy * kTH;
     const int64_t src0 = (int64_t)f * A.in_sn;
 
@@ -214,6 +213,7 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + kTH - 1) / kTH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   auto kern = ravu_kernel<R, C, KEYMODE, NT, LH, OF32>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

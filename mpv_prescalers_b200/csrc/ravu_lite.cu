@@ -167,10 +167,8 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
 
   // one thread asks the TMA engine for the (SW x SH) box of `tile` (origin may be negative: OOB -> 0)
   const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);  // address of the __grid_constant__ parameter itself
-  auto tma_issue = [&, tmap_ptr](long long tile, int buf) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+  auto tma_issue = [&, tmap_ptr](const TileWalk& tw, int buf) {
+    const int tix = tw.tix, tiy = tw.tiy, f = tw.f;
     const uint32_t bar = smem_addr(&s_mbar[buf]);
     const uint32_t dst = smem_addr(s_tiles + buf * TBUF);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PLANE * 4) : "memory");
@@ -179,17 +177,18 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
         "l"(tmap_ptr), "r"(tix * kTW - XO), "r"(tiy * TH - O), "r"(f), "r"(bar)
         : "memory");
   };
+  TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);   // the tile being computed
+  TileWalk ahead = walk;                                        // the tile being fetched (one step ahead)
   if constexpr (TMA) {
     if (tid < 32 && blockIdx.x < A.total_tiles) {
-      if (elect_one()) tma_issue(blockIdx.x, 0);
+      if (elect_one()) tma_issue(ahead, 0);
     }
   }
+  ahead.next();
 
   uint32_t it = 0;
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it, walk.next(), ahead.next()) {
+    const int tix = walk.tix, tiy = walk.tiy, f = walk.f;
     const int x0 = tix * kTW, y0 = tiy * TH;
     const int64_t src0 = (int64_t)f * A.in_sn;   // element offset of this frame
     float* __restrict__ s_tile = s_tiles + (TMA ? (it & 1) * TBUF : 0);
@@ -197,7 +196,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
     if constexpr (TMA) {
       // the other buffer was released by the barrier that ended the previous iteration
       if (tid < 32 && tile + gridDim.x < A.total_tiles) {
-        if (elect_one()) tma_issue(tile + gridDim.x, (it + 1) & 1);
+        if (elect_one()) tma_issue(ahead, (it + 1) & 1);
       }
       mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
       const bool edge = x0 - XO < 0 || y0 - O < 0 || x0 - XO + SW > A.w || y0 - O + SH > A.h;
@@ -458,6 +457,7 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + TH - 1) / TH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   bool use_tma = false;

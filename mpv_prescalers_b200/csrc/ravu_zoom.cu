@@ -112,10 +112,9 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
   const int tid = threadIdx.x;
   static_assert(kTOW == 32 && kTOH == 32 && kNT == 256, "the patch mapping below assumes 32x32 tiles and 8 warps");
 
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
-    const int tix = (int)(tile % A.tiles_x);
-    const int tiy = (int)((tile / A.tiles_x) % A.tiles_y);
-    const int f = (int)(tile / ((long long)A.tiles_x * A.tiles_y));
+  TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next()) {
+    const int tix = walk.tix, tiy = walk.tiy, f = walk.f;
     const int ox0 = tix * kTOW, oy0 = tiy * kTOH;
     const int64_t src0 = (int64_t)f * A.in_sn;
 
@@ -276,6 +275,7 @@ int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   a.tiles_x = (a.ow + kTOW - 1) / kTOW;
   a.tiles_y = (a.oh + kTOH - 1) / kTOH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
+  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   auto kern = ravu_zoom_kernel<R, C, KEYMODE, AR, LUTH, TEXF>;
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, 0));
