@@ -34,7 +34,20 @@ struct RavuArgs {
   mpvp_key_params key;
 };
 
-constexpr int kTW = 64, kTH = 32;
+#ifndef MPVP_X_RAVU_TH1
+#define MPVP_X_RAVU_TH1 64
+#endif
+#ifndef MPVP_X_RAVU_TH3
+#define MPVP_X_RAVU_TH3 48
+#endif
+constexpr int kTW = 64;
+// tile height: the int11 halo (2r-1 rows and columns are recomputed per tile) costs (64+7)(TH+7)/(64 TH) of phase A:
+// 1.35x at TH = 32, 1.23x at TH = 64 (ravu-r3 1.91 -> 1.66 ms, TH = 128: 1.63); three-channel tiles (4 planes of
+// HOOKED + int11) fit shared memory up to TH = 56
+template <int C>
+struct TileH {
+  static constexpr int v = C == 1 ? MPVP_X_RAVU_TH1 : MPVP_X_RAVU_TH3;
+};
 constexpr float kCp0 = 0.2126f, kCp1 = 0.7152f, kCp2 = 0.0722f;
 
 __device__ __forceinline__ float rgb_luma(float r, float g, float b) {
@@ -92,6 +105,7 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* 
 template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32>
 __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
   constexpr int N = 2 * R, TAPS = N * N;
+  constexpr int kTH = TileH<C>::v;
   constexpr int LW = (TAPS / 2 + 3) / 4;
   constexpr int LWP = LW | 1;
   constexpr int HH = 2 * R - 1;              // HOOKED halo
@@ -206,6 +220,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
 template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32>
 int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   constexpr int N = 2 * R, TAPS = N * N, LW = ((TAPS / 2 + 3) / 4) | 1, HH = 2 * R - 1;  // LW: padded pitch
+  constexpr int kTH = TileH<C>::v;
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
   const size_t smem = (((LH ? sizeof(uint2) : sizeof(float4)) * 648 * LW + 15) & ~(size_t)15) +
                       sizeof(float) * NP * ((kTW + 2 * HH) * (kTH + 2 * HH) + (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
