@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool memcheck python tools/sanitize.py
+"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpv_prescalers_b200 import prescale
+
+torch.manual_seed(0)
+cases = [
+    ("ravu-lite-ar-r3.hook", (2, 70, 200), None, {}),          # TMA path (width % 4 == 0)
+    ("ravu-lite-ar-r3.hook", (1, 37, 61), None, {}),           # plain staging (odd width)
+    ("ravu-lite-r4.hook", (1, 40, 132), None, {}),
+    ("ravu-lite-ar-r2.hook", (1, 33, 64), None, {"out_dtype": torch.float16}),
+    ("compute/ravu-3x-r3.hook", (1, 30, 68), None, {}),
+    ("compute/ravu-3x-r2-rgb.hook", (1, 3, 30, 50), None, {}),
+    ("ravu-r4.hook", (1, 70, 90), None, {}),
+    ("ravu-r3-rgb.hook", (1, 3, 50, 70), None, {}),
+    ("ravu-zoom-r3.hook", (1, 40, 60), (97, 151), {}),
+    ("ravu-zoom-ar-r2-rgb.hook", (1, 3, 40, 60), (120, 180), {}),
+    ("nnedi3-nns256-win8x6.hook", (1, 40, 70), None, {}),
+    ("nnedi3-nns32-win8x4.hook", (2, 40, 70), None, {}),
+    ("nnedi3-nns64-win8x6.hook", (1, 40, 70), None, {}),
+]
+for hook, shape, osz, kw in cases:
+    x = torch.rand(*shape, device="cuda")
+    out = prescale(x, hook, output_size=osz, **kw)
+    torch.cuda.synchronize()
+    print(hook, tuple(out.shape), "ok")
+u8 = torch.randint(0, 256, (2, 48, 80), dtype=torch.uint8, device="cuda")
+for hook in ("ravu-lite-ar-r3.hook", "ravu-r3.hook", "nnedi3-nns32-win8x4.hook"):
+    out = prescale(u8, hook)
+    torch.cuda.synchronize()
+    print(hook, "uint8", tuple(out.shape), "ok")
