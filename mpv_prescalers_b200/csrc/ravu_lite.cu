@@ -237,6 +237,23 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       }
     });
     __syncthreads();
+    // the staging above is synchronous (no TMA on this path): pull the rows of the NEXT tile into L2 now, one
+    // 128-byte line per thread, so that its staging loads find them there
+    if (tile + gridDim.x < A.total_tiles) {
+      const int eb = fmt_bytes(A.io.in_fmt);
+      constexpr int LPR = (SW * 4 + 127) / 128 + 1;            // lines per staged row (upper bound)
+      for (int i = tid; i < SH * LPR * C; i += kThreads) {
+        const int c = i / (SH * LPR), r = i - c * (SH * LPR);
+        const int sy = r / LPR, ln = r - sy * LPR;
+        const int gy = clampi(ahead.tiy * TH + sy - O, 0, A.h - 1);
+        const int gx = ahead.tix * kTW - XO + ln * (128 / eb);
+        if (gx < A.w) {
+          const char* ptr = static_cast<const char*>(A.in) +
+                            ((int64_t)ahead.f * A.in_sn + c * A.in_sc + (int64_t)gy * A.in_sy + (gx < 0 ? 0 : gx)) * eb;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
+    }
     }
 
     if constexpr (AR) {
