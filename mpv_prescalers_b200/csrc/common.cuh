@@ -112,6 +112,20 @@ __device__ __forceinline__ float key_diff(int k, SF S) {
   return __fsub_rn(S(0), S(-1));
 }
 
+// The same finite differences selected by an explicit stencil kind (0: 4th order, 1: central, 2: forward, 3: backward)
+template <int N, class SF>
+__device__ __forceinline__ float key_diff_kind(int kind, SF S) {
+  if (kind == 0) {
+    float t = __fmaf_rn(8.0f, S(1), -S(2));
+    t = __fmaf_rn(-8.0f, S(-1), t);
+    t = __fadd_rn(t, S(-2));
+    return div12_rn(t);
+  }
+  if (kind == 1) return __fmul_rn(__fsub_rn(S(1), S(-1)), 0.5f);
+  if (kind == 2) return __fsub_rn(S(1), S(0));
+  return __fsub_rn(S(0), S(-1));
+}
+
 struct KeyOut {
   int row;
 };
@@ -278,6 +292,55 @@ __device__ __forceinline__ int ravu_key2(const mpvp_key_params& kp, WF W) {
     }
     return key_from_abd_fast<NTHR>(kp, ad.x, b, ad.y);
   }
+}
+
+// ---- two RAVU keys whose windows are one column apart ---------------------------------------------------------
+// The int10 / int01 keys of one pixel (ravu-r2.hook:115-316) read windows on the 45-degree lattice that are shifted
+// by ONE step along i: sample (i, j) of the second = sample (i-1, j) of the first.  U(a, j), a in [0, N], j in [0, N),
+// is the union window (first key: column a = i + 1, second key: a = i).  One sweep over the columns evaluates every
+// j-direction stencil once for both keys, and the i-direction stencil once wherever both keys pick the same
+// stencil form (the inner columns); each key's sums still see its own points in the shader's order (i outer, j
+// inner) with individually rounded products, so both rows are bit-identical to two separate ravu_key2 calls.
+__host__ __device__ constexpr int stencil_kind(int k, int n) {
+  return (k - 2 >= 0 && k + 2 <= n - 1) ? 0 : ((k - 1 >= 0 && k + 1 <= n - 1) ? 1 : (k - 1 < 0 ? 2 : 3));
+}
+template <int N, int G, int NTHR, class UF>
+__device__ __forceinline__ void ravu_key_pair(const mpvp_key_params& kp, UF U, int& row_first, int& row_second) {
+  constexpr int O = (N - G) / 2;
+  float2 ad0 = make_float2(0.0f, 0.0f), ad1 = ad0;
+  float b0 = 0.0f, b1 = 0.0f;
+#pragma unroll
+  for (int a = O; a <= O + G; ++a) {
+    const bool use0 = a - 1 >= O && a - 1 < O + G;   // first key: i = a - 1
+    const bool use1 = a < O + G;                      // second key: i = a
+#pragma unroll
+    for (int j = O; j < O + G; ++j) {
+      const float gy = key_diff<STENCIL_RAVU, N>(j, [&](int dd) { return U(a, j + dd); });
+      float gx0 = 0.0f, gx1 = 0.0f;
+      // in the union window the first key's column i sits at a = i + 1, hence the same S for both
+      auto S = [&](int dd) { return U(a + dd, j); };
+      if (use0) gx0 = key_diff_kind<N>(stencil_kind(a - 1, N), S);
+      if (use1) gx1 = (use0 && stencil_kind(a, N) == stencil_kind(a - 1, N)) ? gx0 : key_diff_kind<N>(stencil_kind(a, N), S);
+      if (use0) {
+        const float g = kp.gauss[(a - 1 - O) * G + (j - O)];
+        const float2 gxy = make_float2(gx0, gy);
+        const float2 t = mul2_rn(mul2_rn(gxy, gxy), make_float2(g, g));
+        ad0.x = __fadd_rn(ad0.x, t.x);
+        ad0.y = __fadd_rn(ad0.y, t.y);
+        b0 = __fadd_rn(b0, __fmul_rn(__fmul_rn(gx0, gy), g));
+      }
+      if (use1) {
+        const float g = kp.gauss[(a - O) * G + (j - O)];
+        const float2 gxy = make_float2(gx1, gy);
+        const float2 t = mul2_rn(mul2_rn(gxy, gxy), make_float2(g, g));
+        ad1.x = __fadd_rn(ad1.x, t.x);
+        ad1.y = __fadd_rn(ad1.y, t.y);
+        b1 = __fadd_rn(b1, __fmul_rn(__fmul_rn(gx1, gy), g));
+      }
+    }
+  }
+  row_first = key_from_abd_fast<NTHR>(kp, ad0.x, b0, ad0.y);
+  row_second = key_from_abd_fast<NTHR>(kp, ad1.x, b1, ad1.y);
 }
 
 __device__ __forceinline__ float pow32(float c) {

@@ -55,6 +55,9 @@ __device__ __forceinline__ float rgb_luma(float r, float g, float b) {
   return __fadd_rn(__fadd_rn(__fmul_rn(r, kCp0), __fmul_rn(g, kCp1)), __fmul_rn(b, kCp2));
 }
 
+template <int R, int C, bool LH, class KF, class CF>
+__device__ __forceinline__ void ravu_apply(int row, const void* __restrict__ s_lut_raw, KF KS, CF CS, float (&res)[C]);
+
 // One key + convolution.  KS(t) = key sample t, CS(c, t) = colour sample of channel c.
 // LH: the LUT sits in shared memory as 4 x binary16 per texel (exact, the texels are binary16 values): the
 // per-lane row gather is bank-conflict bound and 8-byte texels need half the wavefronts of 16-byte ones.
@@ -68,6 +71,16 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* 
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) ks[t] = KS(t);
   const int row = ravu_key2<STENCIL_RAVU, N, G, 8, true>(kp, [&](int i, int j) { return ks[i * N + j]; });
+  ravu_apply<R, C, LH>(row, s_lut_raw, [&](int t) { return ks[t]; }, CS, res);
+  return row;
+}
+
+// The convolution of one pass with the weights of LUT row `row`: res = sum_k (s_k + s_{N-1-k}) * w_k, clamp(0, 1)
+template <int R, int C, bool LH, class KF, class CF>
+__device__ __forceinline__ void ravu_apply(int row, const void* __restrict__ s_lut_raw, KF KS, CF CS, float (&res)[C]) {
+  constexpr int N = 2 * R, TAPS = N * N;
+  constexpr int LW = (TAPS / 2 + 3) / 4;
+  constexpr int LWP = LW | 1;
 #pragma unroll
   for (int c = 0; c < C; ++c) res[c] = 0.f;
 #pragma unroll
@@ -88,8 +101,8 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* 
       if (k < TAPS / 2) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float sa = (C == 1) ? ks[k] : CS(c, k);
-          const float sb = (C == 1) ? ks[TAPS - 1 - k] : CS(c, TAPS - 1 - k);
+          const float sa = (C == 1) ? KS(k) : CS(c, k);
+          const float sb = (C == 1) ? KS(TAPS - 1 - k) : CS(c, TAPS - 1 - k);
           res[c] = fmaf(sa + sb, wv[e], res[c]);
         }
       }
@@ -97,7 +110,6 @@ __device__ __forceinline__ int ravu_conv(const mpvp_key_params& kp, const void* 
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) res[c] = fminf(fmaxf(res[c], 0.f), 1.f);
-  return row;
 }
 
 // KEYMODE: 0 luma (C=1), 1 yuv (key = channel 0), 2 rgb (key = BT.709 luma)
@@ -187,19 +199,39 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const float* __restrict__ ib = s_i + (ly + R) * IW + (lx + R);     // int11(x, y)
       float r10[C], r01[C];
       int rows[2];
+      // sample (i, j) of a pass sits at twice-the-real-position (tx2 - (2R-1) + i + j, ty2 - i + j) relative to (2x, 2y),
+      // with (tx2, ty2) = (1, 0) for int10 and (0, 1) for int01: even positions are HOOKED texels, odd ones int11.
+      // The int01 window is the int10 window shifted by one along i (sample (i, j) of int01 = sample (i-1, j) of
+      // int10), so both keys read ONE (N+1) x N register window U[a][j] = int10 sample (a-1, j): the samples are
+      // loaded once, and every gradient / product the two keys have in common (all the j-direction stencils of the
+      // shared columns, the 4th-order i-direction ones of the inner columns) is the SAME expression on the same
+      // registers, which the compiler evaluates once.
+      auto fetch0 = [&](int plane, int ii, int jj) -> float {
+        const int px2 = 1 - (2 * R - 1) + ii + jj, py2 = -ii + jj;
+        if ((px2 & 1) == 0) return hb[plane * HHt * HW_ + (py2 / 2) * HW_ + (px2 / 2)];
+        return ib[plane * IH * IW + ((py2 - 1) / 2) * IW + ((px2 - 1) / 2)];
+      };
+      float U[(N + 1) * N];
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int tx2 = pass == 0 ? 1 : 0, ty2 = pass == 0 ? 0 : 1;
-        // sample t=(i,j): twice the real position = (tx2 - (2R-1) + i + j, ty2 - i + j)
-        auto fetch = [&](int plane, int t) -> float {
-          const int ii = t / N, jj = t % N;
-          const int px2 = tx2 - (2 * R - 1) + ii + jj, py2 = ty2 - ii + jj;
-          if ((px2 & 1) == 0) return hb[plane * HHt * HW_ + (py2 / 2) * HW_ + (px2 / 2)];
-          return ib[plane * IH * IW + ((py2 - 1) / 2) * IW + ((px2 - 1) / 2)];
-        };
-        rows[pass] = ravu_conv<R, C, LH>(
-            A.key, s_lut, [&](int t) { return fetch(KP, t); }, [&](int c, int t) { return fetch(c, t); },
-            pass == 0 ? r10 : r01);
+      for (int a = 0; a <= N; ++a)
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) U[a * N + jj] = fetch0(KP, a - 1, jj);
+      if constexpr (R == 4 && C == 1) {
+        // both keys in one sweep over the union window: ravu-r4 3.41 -> 2.88 ms per 16 frames.  (r2 / r3 share too few
+        // stencils to pay for the second accumulator set, +1..3 %; the 3-channel kernels are bound by their colour
+        // sample loads and do not gain.)
+        ravu_key_pair<N, 6, 8>(A.key, [&](int a, int jj) { return U[a * N + jj]; }, rows[0], rows[1]);
+        ravu_apply<R, C, LH>(rows[0], s_lut, [&](int t) { return U[(t / N + 1) * N + t % N]; },
+                             [&](int c, int t) { return fetch0(c, t / N, t % N); }, r10);
+        ravu_apply<R, C, LH>(rows[1], s_lut, [&](int t) { return U[(t / N) * N + t % N]; },
+                             [&](int c, int t) { return fetch0(c, t / N - 1, t % N); }, r01);
+      } else {
+        rows[0] = ravu_conv<R, C, LH>(
+            A.key, s_lut, [&](int t) { return U[(t / N + 1) * N + t % N]; },
+            [&](int c, int t) { return fetch0(c, t / N, t % N); }, r10);
+        rows[1] = ravu_conv<R, C, LH>(
+            A.key, s_lut, [&](int t) { return U[(t / N) * N + t % N]; },
+            [&](int c, int t) { return fetch0(c, t / N - 1, t % N); }, r01);
       }
       if (A.bucket) {
         A.bucket[(((int64_t)f * 3 + 1) * A.h + y) * A.w + x] = rows[0];
