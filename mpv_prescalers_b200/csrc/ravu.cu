@@ -37,6 +37,12 @@ struct RavuArgs {
 #ifndef MPVP_X_RAVU_TH1
 #define MPVP_X_RAVU_TH1 64
 #endif
+#ifndef MPVP_X_R4_NT1
+#define MPVP_X_R4_NT1 256
+#endif
+#ifndef MPVP_X_R4_NT3
+#define MPVP_X_R4_NT3 384
+#endif
 #ifndef MPVP_X_RAVU_TH3
 #define MPVP_X_RAVU_TH3 48
 #endif
@@ -342,11 +348,11 @@ extern "C" int mpvp_ravu_launch_io(const mpvp_weights* lut, const mpvp_key_param
     case 7: return launch_ravu<2, 3, 1, 512>(a, dev, st);
     case 8: return launch_ravu<2, 3, 2, 512>(a, dev, st);
     case 9: return launch_ravu<3, 1, 0, 512>(a, dev, st);
-    case 10: return launch_ravu<3, 3, 1, 256>(a, dev, st);
-    case 11: return launch_ravu<3, 3, 2, 256>(a, dev, st);
-    case 12: return launch_ravu<4, 1, 0, 256>(a, dev, st);
-    case 13: return launch_ravu<4, 3, 1, 256>(a, dev, st);
-    case 14: return launch_ravu<4, 3, 2, 256>(a, dev, st);
+    case 10: return launch_ravu<3, 3, 1, 512>(a, dev, st);
+    case 11: return launch_ravu<3, 3, 2, 512>(a, dev, st);
+    case 12: return launch_ravu<4, 1, 0, MPVP_X_R4_NT1>(a, dev, st);
+    case 13: return launch_ravu<4, 3, 1, MPVP_X_R4_NT3>(a, dev, st);
+    case 14: return launch_ravu<4, 3, 2, MPVP_X_R4_NT3>(a, dev, st);
   }
   return MPVP_E_INVALID;
 }
