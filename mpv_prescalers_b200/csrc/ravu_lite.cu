@@ -61,6 +61,12 @@ __device__ __forceinline__ constexpr bool ar_tap(int t) {
 #ifndef MPVP_X_PACKCONV_AR
 #define MPVP_X_PACKCONV_AR 0   // convolution sums as packed FFMA2 in the -ar kernels (FMA-pipe bound: no gain, 3.46 -> 3.60 ms)
 #endif
+#ifndef MPVP_X_R4_BLOCKS
+#define MPVP_X_R4_BLOCKS 1   // CTAs per SM for the r4 2x kernels when the LUT is binary16 (57.6 KB)
+#endif
+#ifndef MPVP_X_AR4_STRIPS
+#define MPVP_X_AR4_STRIPS 4
+#endif
 #ifndef MPVP_X_AR3_BLOCKS
 #define MPVP_X_AR3_BLOCKS 2
 #endif
@@ -117,7 +123,7 @@ __device__ __forceinline__ bool elect_one() {
 // OF32: the output planes are float32 at compile time (the runtime format switch at the store costs 2.8 % on the
 // register-bound -ar kernel: 3.53 vs 3.43 ms); false = any mpvp_io output format.
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH, bool OF32>
-__global__ void __launch_bounds__(kThreads, (R == 4 ? 1 : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
+__global__ void __launch_bounds__(kThreads, (R == 4 ? ((LH && SCALE == 2) ? MPVP_X_R4_BLOCKS : 1) : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
   static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
@@ -593,7 +599,7 @@ extern "C" int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_
     case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
     case 7: return launch_lite<3, true, 2, MPVP_X_AR3_P, MPVP_X_AR3_STRIPS>(a, lut->device, st);  // 64x40 tiles: LUT + tiles + power tile = 103 KB, 2 CTAs/SM
     case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
-    case 9: return launch_lite<4, true, 2, 2, 4>(a, lut->device, st);
+    case 9: return launch_lite<4, true, 2, 2, MPVP_X_AR4_STRIPS>(a, lut->device, st);
   }
   return MPVP_E_INVALID;
 }
