@@ -115,14 +115,22 @@ def prescale_rowsplit(frames: torch.Tensor, hook, output_size, devices: Sequence
     if not pl.applied:
         return prescale(frames, hk, output_size, None, lut_precision, False, is_yuv, **io_kwargs)
     sy = pl.out_size[0] // h if v.family != "nnedi3" else (2 if pl.double_y else 1)
-    outs = []
-    for (a, b, s0, s1), dev in zip(row_bands(h, len(devs)), devs):
+    bands = list(zip(row_bands(h, len(devs)), devs))
+    # 1. every band's source rows go to its GPU FIRST: a peer-to-peer copy is queued on the stream of the GPU that owns
+    #    `frames`, and would otherwise wait behind the kernels of the bands launched there before it
+    parts = []
+    for (a, b, s0, s1), dev in bands:
         if b <= a:
-            outs.append(None)
+            parts.append(None)
             continue
         part = frames[..., s0:s1, :]
-        if part.device != dev:
-            part = part.to(dev, non_blocking=True)      # peer-to-peer when `frames` lives on another GPU
+        parts.append(part if part.device == dev else part.to(dev, non_blocking=True))
+    # 2. the kernels of all bands run concurrently (launches are asynchronous, one GPU each)
+    outs = []
+    for ((a, b, s0, s1), dev), part in zip(bands, parts):
+        if part is None:
+            outs.append(None)
+            continue
         # OUTPUT for the band keeps the frame's scale ratio, so that the //!WHEN expressions (ratios of HOOKED and
         # OUTPUT sizes) decide as they did for the whole frame; a band that decides differently is refused below
         osz = None if output_size is None else (max(1, round(output_size[0] * (s1 - s0) / h)), output_size[1])
