@@ -34,6 +34,9 @@ struct ZoomArgs {
   mpvp_key_params key;
 };
 
+#ifndef MPVP_X_ZOOM_MANUAL
+#define MPVP_X_ZOOM_MANUAL 0
+#endif
 constexpr int kTOW = 32, kTOH = 32, kNT = 256;  // output tile; each thread owns one column and kTOH/8 rows
 
 // Canonical position arithmetic: base texel index and sub-pixel phase of output coordinate o.
@@ -215,7 +218,9 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
           };
           float4 w4;
           float av[4] = {0.f, 0.f, 0.f, 0.f};
-          if constexpr (TEXF) {
+          // MPVP_X_ZOOM_MANUAL of the B blocks are fetched by explicit loads + fp32 blend even on the texture path, to
+          // take load off the texture data pipe (the binding unit)
+          if (TEXF && blk >= MPVP_X_ZOOM_MANUAL) {
             const float X = (float)(blk * 9) + (m ? ex.um : ex.u), Y = (float)(row * 9) + (m ? ey.um : ey.u);
             w4 = tex2D<float4>(A.tex, X, Y);
             if constexpr (AR) {
