@@ -122,7 +122,10 @@ __device__ __forceinline__ bool elect_one() {
 // shared-memory wavefronts of 16-byte ones (68 vs 133 per 13-texel row on the config-2 planes).
 // OF32: the output planes are float32 at compile time (the runtime format switch at the store costs 2.8 % on the
 // register-bound -ar kernel: 3.53 vs 3.43 ms); false = any mpvp_io output format.
-template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH, bool OF32>
+// RAWB: bytes per element of the plane the TMA engine fetches (4: float32 straight into the tile; 1 / 2: uint8 / uint16
+// video planes into a raw double buffer, converted to the float tile -- raw / in_max, one division per source
+// pixel -- by a pass over the tile once the mbarrier fires).
+template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH, bool OF32, int RAWB = 4>
 __global__ void __launch_bounds__(kThreads, (R == 4 ? ((LH && SCALE == 2) ? MPVP_X_R4_BLOCKS : 1) : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
@@ -141,6 +144,11 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
   constexpr int SH = TH + 2 * O;
   constexpr int PLANE = SW * SH;              // plane 0 = key plane, planes 1..3 = colours (C == 3)
   constexpr int TBUF = ((PLANE * 4 + 127) / 128) * 32;  // floats per TMA buffer (128-byte aligned)
+  constexpr bool RAW = TMA && RAWB != 4;
+  constexpr int XOR_ = 16 / RAWB;             // raw box: starts 16 bytes left of the tile ...
+  constexpr int RW = ((XOR_ + kTW + O + XOR_ - 1) / XOR_) * XOR_;   // ... and spans a multiple of 16 bytes
+  constexpr int RBUF = ((RW * SH * RAWB + 127) / 128) * 32;         // floats per raw buffer (128-byte aligned)
+  static_assert(!RAW || (C == 1), "raw integer staging is single-plane");
   // anti-ringing: ((0.1+l)^32, (1.1-l)^32, (0.1+l)^33, (1.1-l)^33) of every source pixel the tile's diamonds tap,
   // computed ONCE per source pixel into shared memory (the shader recomputes them per output pixel and tap)
   constexpr int AO = O < 2 ? O : 2;           // diamond reach dx^2 + dy^2 <= 4
@@ -151,7 +159,8 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
   uint2* s_luth = reinterpret_cast<uint2*>(smem_raw);
   constexpr int kLutBytes = ((int)(LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LWP + 127) & ~127;
   float* s_tiles = reinterpret_cast<float*>(smem_raw + kLutBytes);
-  float4* s_pow = reinterpret_cast<float4*>(s_tiles + (TMA ? 2 * TBUF : PLANE * (C == 1 ? 1 : 4)));
+  // RAW: [raw buffer 0][raw buffer 1][one float tile]; float32 TMA: [tile 0][tile 1]; plain staging: [planes]
+  float4* s_pow = reinterpret_cast<float4*>(s_tiles + (RAW ? 2 * RBUF + TBUF : (TMA ? 2 * TBUF : PLANE * (C == 1 ? 1 : 4))));
   __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
@@ -176,11 +185,11 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
   auto tma_issue = [&, tmap_ptr](const TileWalk& tw, int buf) {
     const int tix = tw.tix, tiy = tw.tiy, f = tw.f;
     const uint32_t bar = smem_addr(&s_mbar[buf]);
-    const uint32_t dst = smem_addr(s_tiles + buf * TBUF);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PLANE * 4) : "memory");
+    const uint32_t dst = smem_addr(s_tiles + buf * (RAW ? RBUF : TBUF));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(RAW ? RW * SH * RAWB : PLANE * 4) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-        "l"(tmap_ptr), "r"(tix * kTW - XO), "r"(tiy * TH - O), "r"(f), "r"(bar)
+        "l"(tmap_ptr), "r"(tix * kTW - (RAW ? XOR_ : XO)), "r"(tiy * TH - O), "r"(f), "r"(bar)
         : "memory");
   };
   TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);   // the tile being computed
@@ -197,7 +206,7 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
     const int tix = walk.tix, tiy = walk.tiy, f = walk.f;
     const int x0 = tix * kTW, y0 = tiy * TH;
     const int64_t src0 = (int64_t)f * A.in_sn;   // element offset of this frame
-    float* __restrict__ s_tile = s_tiles + (TMA ? (it & 1) * TBUF : 0);
+    float* __restrict__ s_tile = s_tiles + (RAW ? 2 * RBUF : (TMA ? (it & 1) * TBUF : 0));
 
     if constexpr (TMA) {
       // the other buffer was released by the barrier that ended the previous iteration
@@ -205,6 +214,17 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
         if (elect_one()) tma_issue(ahead, (it + 1) & 1);
       }
       mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
+      if constexpr (RAW) {
+        // raw integer texels -> the float tile (same layout as the float32 TMA tile: XO = 4 columns left of the tile)
+        const unsigned char* __restrict__ rb = reinterpret_cast<const unsigned char*>(s_tiles + (it & 1) * RBUF);
+        for (int i = tid; i < PLANE; i += kThreads) {
+          const int sy = i / SW, sx = i - sy * SW;
+          const int ri = sy * RW + sx + (XOR_ - XO);
+          const float rawv = RAWB == 1 ? (float)rb[ri] : (float)reinterpret_cast<const unsigned short*>(rb)[ri];
+          s_tile[i] = __fdiv_rn(rawv, A.io.in_max);
+        }
+        __syncthreads();
+      }
       const bool edge = x0 - XO < 0 || y0 - O < 0 || x0 - XO + SW > A.w || y0 - O + SH > A.h;
       if (edge) {  // CTA-uniform: replicate the border (clamp-to-edge) over the zero-filled texels
         for (int i = tid; i < PLANE; i += kThreads) {
@@ -454,15 +474,18 @@ bool tma_enabled() {
 
 // 3-D tensor map {w, h, n} over the input planes with a (box_w x box_h x 1) box; false if the layout does not
 // meet TMA's 16-byte rules (then the kernel stages with plain loads)
-bool make_plane_tmap(CUtensorMap* tm, const float* base, int w, int h, int n, int64_t sy, int64_t sn, int box_w, int box_h) {
+bool make_plane_tmap(CUtensorMap* tm, const void* base, int eb, int w, int h, int n, int64_t sy, int64_t sn, int box_w, int box_h) {
   if (!tma_enabled() || !encode_tiled()) return false;
   if (n == 1) sn = (int64_t)h * sy;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (sy * 4) % 16 || (sn * 4) % 16 || sy < w || box_w > 256 || box_h > 256) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (sy * eb) % 16 || (sn * eb) % 16 || sy < w || box_w > 256 || box_h > 256 ||
+      (box_w * eb) % 16)
+    return false;
   const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  const cuuint64_t strides[2] = {(cuuint64_t)sy * 4, (cuuint64_t)sn * 4};
+  const cuuint64_t strides[2] = {(cuuint64_t)sy * eb, (cuuint64_t)sn * eb};
   const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+  const CUtensorMapDataType dt = eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  return encode_tiled()(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -484,16 +507,37 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   bool use_tma = false;
-  if constexpr (C == 1) {  // TMA staging moves float32 texels; other plane formats are converted while staging
-    if (a.io.in_fmt == MPVP_FMT_F32)
-      use_tma = make_plane_tmap(&tmap, static_cast<const float*>(a.in), a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
+  int rawb = 4;   // bytes per element fetched by TMA
+  if constexpr (C == 1) {
+    if (a.io.in_fmt == MPVP_FMT_F32) {
+      use_tma = make_plane_tmap(&tmap, a.in, 4, a.w, a.h, a.n, a.in_sy, a.in_sn, SWT, SH);
+    } else if constexpr (FASTKEY && LH && !OF32) {   // integer video planes: raw TMA fetch + conversion pass
+      if (a.io.in_fmt == MPVP_FMT_U8 || a.io.in_fmt == MPVP_FMT_U16) {
+        rawb = a.io.in_fmt == MPVP_FMT_U8 ? 1 : 2;
+        const int xor_ = 16 / rawb, rw = ((xor_ + kTW + Gm::O + xor_ - 1) / xor_) * xor_;
+        use_tma = make_plane_tmap(&tmap, a.in, rawb, a.w, a.h, a.n, a.in_sy, a.in_sn, rw, SH);
+        if (!use_tma) rawb = 4;
+      }
+    }
   }
   constexpr int AO = Gm::O < 2 ? Gm::O : 2;
   constexpr size_t kPow = AR ? sizeof(float4) * (kTW + 2 * AO) * (TH + 2 * AO) : 0;  // anti-ringing power tile
-  const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LW) + 127) & ~(size_t)127) + (use_tma ? sizeof(float) * 2 * TBUF : sizeof(float) * SW * SH * (C == 1 ? 1 : 4)) + kPow;
+  size_t tiles_bytes = sizeof(float) * SW * SH * (C == 1 ? 1 : 4);
+  if (use_tma) {
+    tiles_bytes = sizeof(float) * 2 * TBUF;
+    if (rawb != 4) {
+      const int xor_ = 16 / rawb, rw = ((xor_ + kTW + Gm::O + xor_ - 1) / xor_) * xor_;
+      tiles_bytes = sizeof(float) * (2 * (size_t)(((rw * SH * rawb + 127) / 128) * 32) + TBUF);
+    }
+  }
+  const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * ROWS * LW) + 127) & ~(size_t)127) + tiles_bytes + kPow;
   auto kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, false, LH, OF32>;
   if constexpr (C == 1) {
     if (use_tma) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH, OF32>;
+    if constexpr (FASTKEY && LH && !OF32) {
+      if (use_tma && rawb == 1) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH, OF32, 1>;
+      if (use_tma && rawb == 2) kern = ravu_lite_kernel<R, AR, SCALE, P, STRIPS, C, KEYMODE, FASTKEY, true, LH, OF32, 2>;
+    }
   }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

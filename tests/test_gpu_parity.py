@@ -206,6 +206,25 @@ def test_integer_input_planes_match_oracle(name, bits):
     _run_ravu_variant(name, n=1, h=48, w=70, config=21, out_hw=out_hw, in_bits=bits)
 
 
+@pytest.mark.parametrize("bits", [8, 10, 16])
+@pytest.mark.parametrize("name", ["ravu-lite-ar-r3.hook", "ravu-lite-r2.hook", "ravu-lite-r4.hook", "compute/ravu-3x-r3.hook"])
+def test_integer_planes_through_raw_tma_staging(name, bits):
+    """Plane widths that meet TMA's 16-byte rules take the raw integer TMA fetch + conversion pass (ravu-lite / 3x
+    luma): several tiles wide and high, so interior, edge and corner tiles (zero-filled halo patched to
+    clamp-to-edge after the conversion) are all covered; integer output so that the generic-store kernels run."""
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _run_ravu_variant(name, n=2, h=100, w=208, config=25, in_bits=bits)
+    # and the integer -> integer route (the kernels the raw staging is compiled for) equals the float32-output result
+    hk = HookFile.parse(hook_path(name))
+    raw, _ = _quantise_planes(_frames(hk.variant, 2, 100, 208, 25), bits)
+    xt = torch.from_numpy(raw).cuda()[:, 0]
+    ref = prescale(xt, hk, out_dtype=torch.float32, bit_depth=bits)
+    got = prescale(xt, hk, bit_depth=bits)
+    mx = float((1 << bits) - 1)
+    assert torch.equal(got.to(torch.float32), torch.round(ref.clamp(0, 1) * mx))
+
+
 @pytest.mark.parametrize("bits", [8, 10])
 def test_integer_input_planes_nnedi3(bits):
     from mpv_prescalers_b200 import HookFile, prescale
