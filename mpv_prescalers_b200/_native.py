@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # MPVP_LIB: load an experiment build (tools/build_variant.py) instead of the product library
 LIB_PATH = os.environ.get("MPVP_LIB") or os.path.join(HERE, "libmpvp.so")
-SOURCES = ["abi.cu", "ravu_lite.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu"]
+SOURCES = ["abi.cu", "ravu_lite.cu", "ravu_lite_ar.cu", "ravu_3x.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
