@@ -38,9 +38,9 @@ extern "C" int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_
   a.key = *key;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (radius * 2 + (ar ? 1 : 0)) {
-    case 4: return launch_lite<2, false, 2, 4, 2>(a, lut->device, st);
+    case 4: return launch_lite<2, false, 2, MPVP_X_LITE_P, MPVP_X_LITE_STRIPS>(a, lut->device, st);
     case 5: return ravu_lite_ar_dispatch(a, radius, lut->device, st);
-    case 6: return launch_lite<3, false, 2, 4, 2>(a, lut->device, st);
+    case 6: return launch_lite<3, false, 2, MPVP_X_LITE_P, MPVP_X_LITE_STRIPS>(a, lut->device, st);
     case 7: return ravu_lite_ar_dispatch(a, radius, lut->device, st);
     case 8: return launch_lite<4, false, 2, 2, 4>(a, lut->device, st);
     case 9: return ravu_lite_ar_dispatch(a, radius, lut->device, st);

@@ -68,6 +68,15 @@ __device__ __forceinline__ constexpr bool ar_tap(int t) {
 #ifndef MPVP_X_PACKCONV_AR
 #define MPVP_X_PACKCONV_AR 0   // convolution sums as packed FFMA2 in the -ar kernels (FMA-pipe bound: no gain, 3.46 -> 3.60 ms)
 #endif
+#ifndef MPVP_X_LITE_BLOCKS
+#define MPVP_X_LITE_BLOCKS 2   // CTAs per SM of the plain (non -ar) r2 / r3 2x kernels
+#endif
+#ifndef MPVP_X_LITE_P
+#define MPVP_X_LITE_P 4
+#endif
+#ifndef MPVP_X_LITE_STRIPS
+#define MPVP_X_LITE_STRIPS 2
+#endif
 #ifndef MPVP_X_R4_BLOCKS
 #define MPVP_X_R4_BLOCKS 1   // CTAs per SM for the r4 2x kernels when the LUT is binary16 (57.6 KB)
 #endif
@@ -133,7 +142,7 @@ __device__ __forceinline__ bool elect_one() {
 // video planes into a raw double buffer, converted to the float tile -- raw / in_max, one division per source
 // pixel -- by a pass over the tile once the mbarrier fires).
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool TMA, bool LH, bool OF32, int RAWB = 4>
-__global__ void __launch_bounds__(kThreads, (R == 4 ? ((LH && SCALE == 2) ? MPVP_X_R4_BLOCKS : 1) : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : 2)))
+__global__ void __launch_bounds__(kThreads, (R == 4 ? ((LH && SCALE == 2) ? MPVP_X_R4_BLOCKS : 1) : ((AR && R == 3) ? MPVP_X_AR3_BLOCKS : ((!AR && SCALE == 2) ? MPVP_X_LITE_BLOCKS : 2))))
 ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || C == 1, "TMA staging is implemented for single-plane inputs");
   static_assert(C == 1 || SCALE == 3, "3-channel planes exist only for RAVU-3x");
