@@ -7,7 +7,7 @@ The per-neuron dot products are restated as one ``[pixels x K] @ [K x nns]`` con
 weight set (<= 5e-6 from the literal neuron-serial order).
 
 PARITY PIN: checked against ``oracle/glsl_exec.py`` (literal execution of the shader text) in
-``tests/test_oracle_vs_glsl.py`` with tolerance 2e-5; no reference golden vectors exist
+``tests/test_oracle.py`` with tolerance 2e-5; no reference golden vectors exist
 (parity against the reference's own outputs is UNPINNED).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline leg may import this.

@@ -10,7 +10,7 @@ Follows, operation by operation, the GLSL of the reference's root variants:
 * ravu-zoom: ``ravu-zoom-r2.hook:23-134``, AR ``ravu-zoom-ar-r2.hook:24-208``;
 * ravu-3x: ``compute/ravu-3x-r2.hook:15-115``.
 
-PARITY PIN: ``tests/test_oracle_vs_glsl.py`` checks this file against ``oracle/glsl_exec.py``
+PARITY PIN: ``tests/test_oracle.py`` checks this file against ``oracle/glsl_exec.py``
 (literal execution of the shader text) -- bit-exact for every RAVU family.  There are no golden
 vectors in the reference and it cannot be run here, so against the reference's own outputs parity is
 UNPINNED.
