@@ -37,6 +37,9 @@ struct RavuArgs {
 #ifndef MPVP_X_RAVU_TH1
 #define MPVP_X_RAVU_TH1 64
 #endif
+#ifndef MPVP_X_R23_NT1
+#define MPVP_X_R23_NT1 512
+#endif
 #ifndef MPVP_X_R4_NT1
 #define MPVP_X_R4_NT1 256
 #endif
@@ -344,10 +347,10 @@ extern "C" int mpvp_ravu_launch_io(const mpvp_weights* lut, const mpvp_key_param
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dev = lut->device;
   switch (radius * 3 + key_mode) {
-    case 6: return launch_ravu<2, 1, 0, 512>(a, dev, st);
+    case 6: return launch_ravu<2, 1, 0, MPVP_X_R23_NT1>(a, dev, st);
     case 7: return launch_ravu<2, 3, 1, 512>(a, dev, st);
     case 8: return launch_ravu<2, 3, 2, 512>(a, dev, st);
-    case 9: return launch_ravu<3, 1, 0, 512>(a, dev, st);
+    case 9: return launch_ravu<3, 1, 0, MPVP_X_R23_NT1>(a, dev, st);
     case 10: return launch_ravu<3, 3, 1, 512>(a, dev, st);
     case 11: return launch_ravu<3, 3, 2, 512>(a, dev, st);
     case 12: return launch_ravu<4, 1, 0, MPVP_X_R4_NT1>(a, dev, st);
