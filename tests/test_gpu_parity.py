@@ -225,6 +225,23 @@ def test_integer_planes_through_raw_tma_staging(name, bits):
     assert torch.equal(got.to(torch.float32), torch.round(ref.clamp(0, 1) * mx))
 
 
+@pytest.mark.parametrize("hw", [(1, 16), (16, 16), (5, 32), (33, 48), (64, 80), (70, 144), (41, 272)])
+@pytest.mark.parametrize("name", ["ravu-lite-ar-r3.hook", "ravu-lite-r4.hook", "compute/ravu-3x-r2.hook"])
+def test_integer_planes_raw_tma_edge_sizes(name, hw):
+    """TMA-eligible integer planes smaller than, equal to and straddling the 64-pixel tiles (the TMA box is wider than
+    the plane, every tile is an edge tile): the integer -> integer kernels (raw TMA fetch, conversion pass, edge
+    patch) must equal the float32-output kernels (plain converting loads) pushed through the store rule."""
+    from mpv_prescalers_b200 import prescale
+
+    _need_gpu()
+    g = torch.Generator().manual_seed(hw[0] * 1000 + hw[1])
+    for dt, bits in ((torch.uint8, 8), (torch.uint16, 10)):
+        x = torch.randint(0, 1 << bits, (2, hw[0], hw[1]), dtype=torch.int32, generator=g).to(dt).cuda()
+        ref = prescale(x, hook_path(name), out_dtype=torch.float32, bit_depth=bits)
+        got = prescale(x, hook_path(name), bit_depth=bits)
+        assert torch.equal(got.to(torch.float32), torch.round(ref.clamp(0, 1) * float((1 << bits) - 1)))
+
+
 @pytest.mark.parametrize("bits", [8, 10])
 def test_integer_input_planes_nnedi3(bits):
     from mpv_prescalers_b200 import HookFile, prescale
