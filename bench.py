@@ -156,39 +156,216 @@ def _cpu_one(args):
 
 
 def cpu_baseline(wl, budget_s=20.0, procs=1):
-    """Time the oracle (a port of the reference's shader math) on a bounded sample of the workload."""
-    import numpy as np
-
+    """Time the oracle (a port of the reference's shader math) on a bounded sample of the workload, one process."""
     hook, c, h, w, _, fac, _ = WORKLOADS[wl]
     # nnedi3 at 2160p is minutes per frame on a CPU: use a crop of the same planes
     crop = (270, 480) if hook.startswith("nnedi3") else (h, w)
-    frames = cpu_frames(wl, max(procs, 1))[:, :, : crop[0], : crop[1]]
+    frames = cpu_frames(wl, 1)[:, :, : crop[0], : crop[1]]
     t0 = time.perf_counter()
     done_px, used = 0, 0
-    if procs <= 1:
-        while True:
-            dt, px = _cpu_one((wl, frames[used % len(frames)]))
-            done_px += px
-            used += 1
-            if time.perf_counter() - t0 > budget_s * 0.5 or used >= 4:
-                break
-        wall = time.perf_counter() - t0
-    else:
-        import multiprocessing as mp
-
-        with mp.get_context("spawn").Pool(procs) as pool:
-            pool.map(_cpu_one, [(wl, frames[i]) for i in range(procs)])  # warm (imports, page-in)
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_one, [(wl, frames[i]) for i in range(procs)])
-            wall = time.perf_counter() - t0
-        done_px, used = sum(r[1] for r in res), procs
+    while True:
+        dt, px = _cpu_one((wl, frames[used % len(frames)]))
+        done_px += px
+        used += 1
+        if time.perf_counter() - t0 > budget_s * 0.5 or used >= 4:
+            break
+    wall = time.perf_counter() - t0
     return {
         "value": done_px / 1e6 / wall,
         "unit": "Mpix/s",
-        "cores": procs,
+        "cores": 1,
         "kind": "port",
-        "sample": f"{used} frame(s) of {crop[1]}x{crop[0]} from the same synthetic workload, NumPy fp32 oracle, {procs} process(es)",
+        "sample": f"{used} frame(s) of {crop[1]}x{crop[0]} from the same synthetic workload, NumPy fp32 oracle, 1 process",
     }
+
+
+def config_of(wl, nf, world, io):
+    hook, c, h, w, _, fac, cfg_idx = WORKLOADS[wl]
+    oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
+    big = 1.0 * c * nf * (IO_MODES[io][0] * h * w + IO_MODES[io][1] * oh * ow) > 2.5e8
+    return {
+        "workload": f"{hook} {w}x{h}->{ow}x{oh} {'luma' if c == 1 else '3ch'} {'fp32' if io == 'f32' else 'planes ' + io}, {nf} frames per GPU (BASELINE.json configs[{cfg_idx}])",
+        "frames_per_gpu": nf,
+        "parallelism": f"frame-sharded x{world}, no collective",
+        "l2": "working set per step exceeds the 126 MB L2" if big else "L2 flushed between steps",
+        "io": io,
+    }
+
+
+def reference_arm(args, wl, nf, world):
+    """--impl reference: the reference's CPU implementation of the path = the NumPy restatement of its shader math
+    (oracle/; the GLSL itself needs mpv + GL/Vulkan, which this image lacks), on all host cores.  A step = one bounded
+    sample of the workload: every process runs the oracle on one crop of a synthetic frame of the workload."""
+    import multiprocessing as mp
+
+    hook, c, h, w, _, fac, _ = WORKLOADS[wl]
+    procs = os.cpu_count() or 1
+    # sized so that W warm-up + K timed steps end within a few minutes: half-height crops (quarter for nnedi3)
+    crop = (270, 480) if hook.startswith("nnedi3") else (max(h // 2, 1), w)
+    frames = cpu_frames(wl, procs)[:, :, : crop[0], : crop[1]]
+    work = [(wl, frames[i]) for i in range(procs)]
+    warm = max(args.warmup, 1)
+    per_step = []
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for _ in range(warm):
+            pool.map(_cpu_one, work)
+        for _ in range(max(args.steps, 1)):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_one, work)
+            per_step.append((time.perf_counter() - t0, sum(r[1] for r in res)))
+    wall = sum(t for t, _ in per_step)
+    val = sum(px for _, px in per_step) / 1e6 / wall
+    sample = (f"per step: {procs} crop(s) of {crop[1]}x{crop[0]} from the synthetic frames of the workload, NumPy fp32 oracle, "
+              f"{procs} processes (one per host core)")
+    return {
+        "impl": "reference", "metric": "output Mpix/s", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": len(per_step),
+        "warmup": args.warmup, "ms_per_step": wall / len(per_step) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(wl, nf, world, args.io),
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = NumPy restatement of the reference's GLSL (oracle/); the GLSL itself needs mpv + GL/Vulkan, which this image lacks",
+    }
+
+
+class Runner:
+    """One workload on this rank's GPU: device-timed steps, roofline, end-to-end through prescale()."""
+
+    def __init__(self, wl, nf, io, rank, world, local_rank, dist):
+        import torch
+
+        from mpv_prescalers_b200 import HookFile, find_hook
+        from mpv_prescalers_b200.api import PlaneIO, plan, upload_weights
+        from mpv_prescalers_b200.synth import torch_batch
+
+        self.torch, self.wl, self.nf, self.io, self.rank, self.world, self.dist = torch, wl, nf, io, rank, world, dist
+        hook, c, h, w, _, fac, cfg_idx = WORKLOADS[wl]
+        self.dev = torch.device("cuda", local_rank)
+        self.local_rank = local_rank
+        self.hk = HookFile.parse(find_hook(hook))
+        self.out_size = None if isinstance(fac, int) else fac
+        self.oh, self.ow = (h * fac, w * fac) if isinstance(fac, int) else fac
+        self.c = c
+        self.pl = plan(self.hk, (h, w), self.out_size)
+        self.W = upload_weights(self.hk, local_rank)
+        x = torch_batch(nf, c, h, w, self.dev, seed=1000 * cfg_idx + rank)
+        self.io_kw = {}
+        if io == "u8":
+            x = torch.round(x.clamp(0, 1) * 255.0).to(torch.uint8)
+        elif io == "u10":
+            x = torch.round(x.clamp(0, 1) * 1023.0).to(torch.int32).to(torch.uint16)
+            self.io_kw = dict(bit_depth=10)
+        elif io == "f16out":
+            self.io_kw = dict(out_dtype=torch.float16)
+        self.x = x
+        self.pio = PlaneIO(x.dtype, self.io_kw.get("out_dtype"), self.io_kw.get("bit_depth"))
+        self.config = config_of(wl, nf, world, io)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, steps, warmup):
+        """(ms_per_step max over ranks, launches, clocks, wall seconds of the timed region)"""
+        torch = self.torch
+        from mpv_prescalers_b200 import _native
+        from mpv_prescalers_b200.api import _launch
+        from mpv_prescalers_b200.sharding import max_over_ranks
+
+        lib = _native.lib()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev) if "flushed" in self.config["l2"] else None
+
+        def step():
+            out, _ = _launch(self.hk, self.pl, self.x, self.W, False, self.pio)
+            return out
+
+        for _ in range(warmup):
+            out = step()
+            if flush is not None:
+                flush.zero_()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            sampler.start()
+        launches0 = lib.mpvp_launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(steps):
+            if flush is not None:
+                flush.zero_()
+            evs[i][0].record()
+            out = step()
+            evs[i][1].record()
+        self.barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = lib.mpvp_launch_count() - launches0
+        clocks = sampler.stop() if self.rank == 0 else None
+        total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), self.dev)
+        del out, flush
+        return total_ms / steps, int(launches), clocks, t_wall
+
+    def roofline(self, ms_per_step, launches_per_step):
+        mpix, abytes, aflops = algorithmic_work(self.wl, self.nf, self.io)
+        hbm_peak, tc_peak, src = peaks()
+        if aflops > 0:
+            ach = aflops / (ms_per_step / 1e3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
+                    "peak_source": src, "hbm_frac": abytes / (ms_per_step / 1e3) / 1e9 / hbm_peak}
+        else:
+            ach = abytes / (ms_per_step / 1e3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": src}
+        roof["kernel"] = f"{self.pl.family} fused kernel(s), {launches_per_step} launch(es) per step, avg {ms_per_step / launches_per_step:.4f} ms"
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr) and self.io == "f32":
+            try:
+                with open(tr) as f:
+                    roof["traffic"] = json.load(f).get(self.wl)
+            except Exception:
+                pass
+        return roof
+
+    def e2e(self, steps, x=None, io_kw=None, copy_floor=True):
+        """The same step through the public prescale() with pinned HOST buffers: H2D, kernel(s), D2H inside the timed
+        region.  copy_floor_ms = the bare pinned H2D + D2H copies of the same bytes on two streams (no kernel): what
+        the box's PCIe path allows."""
+        torch = self.torch
+        from mpv_prescalers_b200 import prescale
+        from mpv_prescalers_b200.sharding import max_over_ranks
+
+        x = self.x if x is None else x
+        io_kw = self.io_kw if io_kw is None else io_kw
+        mpix = self.nf * self.oh * self.ow / 1e6
+        xh = x.cpu().pin_memory()
+        out_dtype = io_kw.get("out_dtype", x.dtype)
+        oh_pinned = torch.empty((self.nf, self.c, self.oh, self.ow), dtype=out_dtype, pin_memory=True)
+        o = prescale(xh, self.hk, self.out_size, out=oh_pinned, **io_kw)  # warm-up (allocator pools, streams)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            o = prescale(xh, self.hk, self.out_size, out=oh_pinned, **io_kw)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, self.dev)
+        res = {"value": mpix * self.world * steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
+               "d2h_bytes_per_step": int(o.numel() * o.element_size()), "steps": steps, "ms_per_step": dt / steps * 1e3}
+        if copy_floor:
+            dx = torch.empty_like(x)
+            do = torch.empty((self.nf, self.c, self.oh, self.ow), dtype=out_dtype, device=self.dev)
+            s1, s2 = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+            for rep in range(2):   # first pass warms up, second is timed
+                self.barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s1):
+                    dx.copy_(xh, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    oh_pinned.copy_(do, non_blocking=True)
+                s1.synchronize()
+                s2.synchronize()
+                fl = time.perf_counter() - t0
+            res["copy_floor_ms"] = max_over_ranks(fl, self.dev) * 1e3
+            del dx, do
+        del o, xh, oh_pinned
+        return res
 
 
 def main():
@@ -202,6 +379,10 @@ def main():
     ap.add_argument("--io", default="f32", choices=["f32", "u8", "u10", "f16out"],
                     help="plane formats either side of the path: f32 (BASELINE.json's), u8 / u10 = UNORM video planes in "
                          "and out (uint8, 10 bits in uint16), f16out = float32 in, binary16 out (SURVEY.md 8f rank 1)")
+    ap.add_argument("--secondary", default="auto",
+                    help="comma-separated workloads timed in the same process after the headline one and reported under "
+                         "'secondary'; 'auto' = the other kernels BASELINE.json's metric and configs name (default workload "
+                         "only), 'none' = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,43 +391,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = args.workload
-    hook, c, h, w, nf_default, fac, cfg_idx = WORKLOADS[wl]
-    nf = args.frames or nf_default
-    oh, ow = (h * fac, w * fac) if isinstance(fac, int) else fac
-    config = {
-        "workload": f"{hook} {w}x{h}->{ow}x{oh} {'luma' if c == 1 else '3ch'} {'fp32' if args.io == 'f32' else 'planes ' + args.io}, {nf} frames per GPU (BASELINE.json configs[{cfg_idx}])",
-        "frames_per_gpu": nf,
-        "parallelism": f"frame-sharded x{world}, no collective",
-        "l2": "working set per step exceeds the 126 MB L2" if 1.0 * c * nf * (IO_MODES[args.io][0] * h * w + IO_MODES[args.io][1] * oh * ow) > 2.5e8 else "L2 flushed between steps",
-    }
+    nf = args.frames or WORKLOADS[wl][4]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        procs = os.cpu_count() or 1
-        base = cpu_baseline(wl, procs=procs)
-        steps = []
-        for _ in range(max(0, args.steps - 1)):
-            steps.append(cpu_baseline(wl, procs=procs)["value"])
-        vals = [base["value"]] + steps
-        val = sum(vals) / len(vals)
-        base["value"] = val
-        line = {
-            "impl": "reference", "metric": "output Mpix/s", "value": val, "unit": "Mpix/s", "n_gpus": 0, "steps": len(vals),
-            "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config, "cpu_baseline": base,
-            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = NumPy restatement of the reference's GLSL (oracle/), the GLSL itself needs mpv+GL/Vulkan which this image lacks",
-        }
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(args, wl, nf, world)))
         return 0
 
     import torch
-
-    from mpv_prescalers_b200 import HookFile, _native, find_hook, prescale
-    from mpv_prescalers_b200.api import plan, upload_weights, _launch
-    from mpv_prescalers_b200.sharding import max_over_ranks
-    from mpv_prescalers_b200.synth import torch_batch
 
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
@@ -259,115 +412,67 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    hk = HookFile.parse(find_hook(hook))
-    out_size = None if isinstance(fac, int) else fac
-    pl = plan(hk, (h, w), out_size)
-    W = upload_weights(hk, local_rank)
-    x = torch_batch(nf, c, h, w, dev, seed=1000 * cfg_idx + rank)
-    from mpv_prescalers_b200.api import PlaneIO
-
-    io_kw = {}
-    if args.io == "u8":
-        x = torch.round(x.clamp(0, 1) * 255.0).to(torch.uint8)
-    elif args.io == "u10":
-        x = torch.round(x.clamp(0, 1) * 1023.0).to(torch.int32).to(torch.uint16)
-        io_kw = dict(bit_depth=10)
-    elif args.io == "f16out":
-        io_kw = dict(out_dtype=torch.float16)
-    pio = PlaneIO(x.dtype, io_kw.get("out_dtype"), io_kw.get("bit_depth"))
-    lib = _native.lib()
-    flush = None
-    if "flushed" in config["l2"]:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step():
-        out, _ = _launch(hk, pl, x, W, False, pio)
-        return out
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        out = step()
-        if flush is not None:
-            flush.zero_()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = lib.mpvp_launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        evs[i][0].record()
-        out = step()
-        evs[i][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = lib.mpvp_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = sum(kernel_ms)
-    total_ms = max_over_ranks(total_ms, dev)
-    ms_per_step = total_ms / args.steps
-    mpix, abytes, aflops = algorithmic_work(wl, nf, args.io)
+    warm = max(args.warmup, 3)
+    run = Runner(wl, nf, args.io, rank, world, local_rank, dist)
+    ms_per_step, launches, clocks, t_wall = run.timed(args.steps, warm)
+    mpix, _, _ = algorithmic_work(wl, nf, args.io)
     value = mpix * world / (ms_per_step / 1e3)
+    roof = run.roofline(ms_per_step, max(1, launches // max(args.steps, 1)))
 
-    hbm_peak, tc_peak, src = peaks()
-    launches_per_step = max(1, launches // max(args.steps, 1))
-    if aflops > 0:
-        ach = aflops / (ms_per_step / 1e3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
-                "peak_source": src, "hbm_frac": abytes / (ms_per_step / 1e3) / 1e9 / hbm_peak}
-    else:
-        ach = abytes / (ms_per_step / 1e3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": src}
-    roof["kernel"] = f"{pl.family} fused kernel, {launches_per_step} launch(es) per step, avg {ms_per_step / launches_per_step:.4f} ms"
-    tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
-        try:
-            with open(tr) as f:
-                roof["traffic"] = json.load(f).get(wl) if args.io == "f32" else None
-        except Exception:
-            pass
-
-    # ---- end to end: pinned host input -> H2D -> kernel -> D2H, through the public prescale() ----------
-    e2e = None
+    e2e = e2e_u8 = None
     if not args.no_e2e:
-        xh = x.cpu().pin_memory()
-        e2e_steps = max(1, min(args.steps, 3))
-        oh_pinned = torch.empty((nf, c, oh, ow), dtype=pio.out_dtype, pin_memory=True)
-        o = prescale(xh, hk, out_size, out=oh_pinned, **io_kw)  # warm-up (allocator pools, streams)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            o = prescale(xh, hk, out_size, out=oh_pinned, **io_kw)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt, dev)
-        e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
-               "d2h_bytes_per_step": int(o.numel() * o.element_size()), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3}
-        del o, xh, oh_pinned
+        e2e = run.e2e(max(1, min(args.steps, 3)))
+        if args.io == "f32" and wl == "ravu-lite-ar-r3":
+            # the same frames as 8-bit video planes in and out (the wire format either side of the path)
+            x8 = torch.round(run.x.clamp(0, 1) * 255.0).to(torch.uint8)
+            e2e_u8 = run.e2e(max(1, min(args.steps, 3)), x=x8, io_kw={})
+            del x8
+    del run
+    torch.cuda.empty_cache()
+
+    # ---- the other kernels of BASELINE.json's metric / configs, in the same process ---------------------------------
+    secondary = []
+    names = []
+    if args.secondary == "auto":
+        if wl == "ravu-lite-ar-r3" and args.io == "f32" and not args.frames:
+            names = ["nnedi3-nns256-win8x6", "ravu-r4", "ravu-r3-rgb", "ravu-zoom-r3", "ravu-zoom-ar-r2", "ravu-3x-r3"]
+    elif args.secondary != "none":
+        names = [n for n in args.secondary.split(",") if n]
+    for name in names:
+        entry = {"workload": name}
+        try:
+            r2 = Runner(name, WORKLOADS[name][4], "f32", rank, world, local_rank, dist)
+            steps2 = max(5, min(args.steps, 20))
+            ms2, l2, ck2, _ = r2.timed(steps2, warm)
+            mp2, _, _ = algorithmic_work(name, r2.nf, "f32")
+            entry.update({"config": r2.config, "value": mp2 * world / (ms2 / 1e3), "unit": "Mpix/s", "ms_per_step": ms2, "steps": steps2,
+                          "warmup": warm, "roofline": r2.roofline(ms2, max(1, l2 // steps2)), "gpu_launches": l2, "clocks": ck2})
+            if not args.no_e2e and name == "nnedi3-nns256-win8x6":
+                entry["e2e"] = r2.e2e(2, copy_floor=False)
+            del r2
+            torch.cuda.empty_cache()
+        except Exception as e:  # a secondary workload must never take the headline line down with it
+            entry["error"] = f"{type(e).__name__}: {e}"[:300]
+        secondary.append(entry)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(wl, procs=1)
+        cpu = cpu_baseline(wl)
 
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         line = {
-            "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config, io=args.io), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "wall_s_timed_region": t_wall,
+            "data": "synthetic", "config": config_of(wl, nf, world, args.io), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if e2e_u8 is not None:
+            line["e2e_u8_planes"] = e2e_u8
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     return 0
 

@@ -100,6 +100,15 @@ const char* mpvp_last_error(void);
 int mpvp_abi_version(void);
 /* number of kernels launched by this library since load (all threads); for bench bookkeeping */
 uint64_t mpvp_launch_count(void);
+/* TEST HOOK: cap the number of persistent CTAs of every later launch (0 = no cap, the default) so that small planes
+ * make each CTA walk many tiles; returns the previous cap.  Results never depend on it (bit-identical). */
+int mpvp_debug_set_grid_limit(int max_ctas);
+
+/* Fill the derived tables of mpvp_key_params (l1_thr[], n_l1_thr, coh_ratio[]) from the shader constants the caller
+ * has set (strength_thr[] / n_strength_thr or strength_log2_scale, n_strength, coherence_thr[]): the launch entry
+ * points evaluate the (strength, coherence) quantisers on the eigenvalues through these tables and refuse key params
+ * whose tables are missing or inconsistent.  Pure host arithmetic; 0 on success. */
+int mpvp_key_params_finalize(mpvp_key_params* key);
 
 /* ---- weights -------------------------------------------------------------------------- */
 

@@ -32,18 +32,31 @@ def sources() -> List[str]:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _headers() -> List[str]:
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + [
+        os.path.join(HERE, "..", "include", "mpvp.h")]
+
+
+def _obj_path(src: str) -> str:
+    return os.path.join(HERE, "..", "build", "obj", os.path.basename(src) + ".o")
+
+
+def _stale(target: str, deps: List[str]) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mpvp.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def needs_build() -> bool:
+    return _stale(LIB_PATH, sources() + _headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into ``libmpvp.so`` (nvcc cross-compiles without a GPU).
 
-    Each translation unit is compiled to an object in parallel (build/obj), then linked."""
+    Each translation unit is compiled to an object in parallel (build/obj) and only when it or a header it may include
+    is newer than its object; then everything is linked."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -51,18 +64,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise NativeError("nvcc not found; cannot build libmpvp.so")
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(HERE, "..", "build", "obj")
-    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(os.path.join(HERE, "..", "build", "obj"), exist_ok=True)
     cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    hdrs = _headers()
 
     def compile_one(src: str):
-        obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        proc = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        obj = _obj_path(src)
+        if not force and not _stale(obj, [src] + hdrs):
+            return src, obj, None
+        tmp_obj = obj + ".tmp"
+        proc = subprocess.run([nvcc] + cflags + ["-c", "-o", tmp_obj, src], cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode == 0:
+            os.replace(tmp_obj, obj)
         return src, obj, proc
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         results = list(pool.map(compile_one, sources()))
     for src, _, proc in results:
+        if proc is None:
+            continue
         if proc.returncode != 0:
             raise NativeError(f"nvcc failed on {src}:\n" + proc.stdout + proc.stderr)
         if verbose:
@@ -110,6 +130,8 @@ SIGNATURES = {
     "mpvp_last_error": (ctypes.c_char_p, []),
     "mpvp_abi_version": (_i, []),
     "mpvp_launch_count": (ctypes.c_uint64, []),
+    "mpvp_debug_set_grid_limit": (_i, [_i]),
+    "mpvp_key_params_finalize": (_i, [_kp]),
     "mpvp_weights_create_lut": (_i, [_i, _vp, _i, _i, _i, ctypes.POINTER(_vp)]),
     "mpvp_weights_create_nnedi3": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(_vp)]),
     "mpvp_weights_destroy": (_i, [_vp]),

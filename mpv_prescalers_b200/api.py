@@ -183,7 +183,9 @@ def l1_thresholds(v: Variant) -> List[np.float32]:
 def upload_weights(hook: HookFile, device: int, lut_precision: str = "fp16") -> _Weights:
     if lut_precision not in ("fp16", "fp32"):
         raise ValueError("lut_precision must be 'fp16' or 'fp32'")
-    key = (hook.path, device, lut_precision)
+    # keyed on CONTENT (LUT payloads / NNEDI3 weights + key constants), not on the path: every parse_text() hook has
+    # the path '<string>', and an edited file keeps its path
+    key = (hook.content_key, device, lut_precision)
     with _wlock:
         hit = _wcache.get(key)
         if hit is not None:
@@ -426,6 +428,8 @@ def prescale(
     if devices is not None:
         from .sharding import prescale_rowsplit, prescale_sharded
 
+        if return_buckets or out is not None:
+            raise ValueError("return_buckets / out cannot be combined with devices=[...] (sharded results stay on their GPUs)")
         if split == "rows":
             return prescale_rowsplit(frames, hk, output_size, list(devices), lut_precision, is_yuv,
                                      out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
@@ -438,9 +442,20 @@ def prescale(
     io = PlaneIO(x.dtype, out_dtype, bit_depth, out_bit_depth)
     pl = plan(hk, (h, w), output_size, is_yuv)
     if not pl.applied:
-        out = frames
-        out.offset, out.applied, out.plan = (0.0, 0.0), False, pl
-        return (out, None) if return_buckets else out
+        # mpv semantics: no pass fired, the plane goes on unchanged.  The caller still gets a tensor of its own (never
+        # an alias it could mutate the input through), of the dtype / in the destination it asked for.
+        if io.out_dtype != io.in_dtype:
+            raise ValueError(f"{hk.name}: no pass fires for this geometry (//!WHEN), so the plane stays {io.in_dtype}; "
+                             f"it cannot be returned as {io.out_dtype}")
+        if out is not None:
+            if tuple(out.shape) != tuple(x.shape) or out.dtype != x.dtype:
+                raise ValueError(f"out must be a {x.dtype} tensor of shape {tuple(x.shape)} (no pass fires: the result is the input)")
+            out.copy_(x)
+            res = _restore_shape(out, in_shape, c)
+        else:
+            res = frames.clone()
+        res.offset, res.applied, res.plan = (0.0, 0.0), False, pl
+        return (res, None) if return_buckets else res
     if not torch.cuda.is_available():
         raise _native.NativeError("prescale() needs a CUDA device: there is no CPU fallback")
     host_input = x.device.type != "cuda"

@@ -50,6 +50,19 @@ struct DeviceGuard {
 
 int sm_count(int device);
 
+// Test hook (mpvp_debug_set_grid_limit): caps the number of persistent CTAs of every launch so that small planes make
+// each CTA / warpgroup walk many tiles -- the steady state of the tile loops (buffer hand-over, mbarrier phase flips,
+// TMEM slot reuse) then runs at sizes the CPU oracle checks in seconds.  0 = no cap (the product setting).
+extern std::atomic<int> g_grid_limit;
+inline long long cap_grid(long long grid) {
+  const int l = g_grid_limit.load(std::memory_order_relaxed);
+  return (l > 0 && grid > l) ? (long long)l : grid;
+}
+
+// The sqrt/division-free key (key_from_abd_fast) reads the DERIVED tables l1_thr[] / coh_ratio[] of mpvp_key_params;
+// a caller that filled only the shader constants must run mpvp_key_params_finalize() first.  MPVP_OK or MPVP_E_INVALID.
+int check_fast_key(const mpvp_key_params* key);
+
 }  // namespace mpvp
 
 // Opaque handle behind mpvp_weights*.
@@ -62,6 +75,9 @@ struct mpvp_weights {
   cudaArray_t lut_arr = nullptr;        // ravu-zoom LUTs only: the binary16 texels as a 2-D array behind a texture object
   cudaTextureObject_t lut_tex = 0;      // FILTER LINEAR, clamp-to-edge, unnormalised coordinates
   int lut_w = 0, lut_h = 0;
+  // ravu-zoom: per-geometry phase plans (member tables + pre-blended phase LUTs), owned by ravu_zoom.cu
+  void* zoom_plans = nullptr;
+  void (*zoom_plans_free)(void*) = nullptr;
   // NNEDI3
   int nns = 0, win_short = 0;
   int nn_group = 16;        // neurons per accumulator block in nn_b (16: 32-column blocks, 8: 16-column blocks)

@@ -125,6 +125,7 @@ int launch_simt(const NnArgs& a0, int device, cudaStream_t stream) {
   }
   long long grid = (long long)sm_count(device) * per_sm;
   if (grid > a.total_tiles) grid = a.total_tiles;
+  grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
   kern<<<(unsigned)grid, kNT, smem, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -150,13 +151,11 @@ int nnedi3_tc(const mpvp_weights* nn, int direction, const void* in, void* out, 
               int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, const IoFmt& io,
               cudaStream_t st);
 
-// MPVP_NNEDI3_IMPL=simt forces the CUDA-core predictor (debugging / cross-checking); default is tcgen05.
+// MPVP_NNEDI3_IMPL=simt forces the CUDA-core predictor (the on-device cross-check of the tensor path, used by
+// tests/test_gpu_parity.py); default is tcgen05.  Read at every launch so that a test can switch it.
 static bool use_simt() {
-  static const bool v = [] {
-    const char* e = getenv("MPVP_NNEDI3_IMPL");
-    return e && e[0] == 's';
-  }();
-  return v;
+  const char* e = getenv("MPVP_NNEDI3_IMPL");
+  return e && e[0] == 's';
 }
 
 }  // namespace mpvp

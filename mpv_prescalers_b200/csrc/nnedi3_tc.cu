@@ -492,301 +492,6 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Pipelined variant for 2*nns >= 256 accumulator columns (nns128 / nns256).
-//
-// Same math and operand layouts as above; what changes is the schedule.  A warpgroup's 128 TMEM columns are
-// TWO 64-column slots.  One job = one tcgen05.mma group of N = 64 (32 neurons) = two tcgen05.ld.x32 blocks.
-// The MMA that refills a slot is issued as soon as the slot's previous contents are in registers, i.e. one
-// whole job (~2000 cycles) before its result is needed, so no MMA latency is exposed and nothing in the
-// steady state is a blocking bar.sync.  (N = 32 jobs were measured 2x slower: every MMA re-reads the 4 KB A
-// slice from shared memory, so small N is shared-memory bound, and the issuing thread's work doubles.)
-//   full[slot]  (count 1, tcgen05.commit)      MMA of the job in `slot` complete
-//   free[slot]  (count 128, one per thread)    every thread has its columns of `slot` in registers
-//   aready[buf] (count 128)                    A operand of the next tile written (double-buffered A)
-// Only the issuing thread ever waits on free[]/aready[].  The A operand of tile i+1 is built in the middle
-// of tile i's epilogue from a warp-private staged window (each warp stages exactly the rows its 32 pixels
-// tap, so staging needs __syncwarp only), and the window of tile i+2 is prefetched with cp.async.
-template <int S, int DIR, int NNS>
-__global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_pipe_kernel(const __grid_constant__ NnTcArgs A) {
-  constexpr int K = 8 * S, KX = K + 16, KC = K / 8, N = 2 * NNS;
-  constexpr int NJ = N / 64;                // MMA jobs per tile
-  static_assert(NJ >= 4 && NJ % 2 == 0, "the two-slot ring assumes at least two turns per tile");
-  constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
-  constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
-  constexpr int SWP = kTileW + HX - 1;      // warp-private staged window: SWP x HY
-  constexpr int WST = (SWP * HY + 3) & ~3;
-  constexpr uint32_t kBBytes = (uint32_t)KX * N * 2;
-  constexpr uint32_t kABytes = (uint32_t)KX * 128 * 2;
-  constexpr int kBarsPerWg = 6;             // full[2], free[2], aready[2]
-
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* s_b = smem;
-  unsigned char* s_a = s_b + kBBytes;                                     // [kWG][2][kABytes]
-  float* s_stage = reinterpret_cast<float*>(s_a + kWG * 2 * kABytes);     // [kWG * 4 warps][WST]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * 4 * WST);  // [kWG][10] + 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + kWG * kBarsPerWg + 1);
-
-  const int tid = threadIdx.x;
-  const int wg = tid >> 7, lt = tid & 127, warp = tid >> 5;
-  const int tx = lt & 31, ty = lt >> 5;
-  // the MMA-issuing thread of warpgroup g is lane 0 of its g-th warp: CTA warps 0, 5, 10, 15, i.e. one per SM
-  // sub-partition (with warp 0 of every group issuing, all four issuers share sub-partition 0 and it becomes the
-  // bottleneck: 7.6 ms instead of 5.3)
-  const bool issuer = lt == 32 * wg;
-
-  const uint32_t mbar_b = smem_u32(s_mbar + kWG * kBarsPerWg);
-  if (tid == 0) {
-    for (int g = 0; g < kWG; ++g) {
-      for (int i = 0; i < 2; ++i) mbar_init(smem_u32(s_mbar + g * kBarsPerWg + i), 1);
-      for (int i = 2; i < 6; ++i) mbar_init(smem_u32(s_mbar + g * kBarsPerWg + i), 128);
-    }
-    mbar_init(mbar_b, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
-  unsigned char* my_a = s_a + wg * 2 * kABytes;
-  {
-    // constant tail of every A row (both buffers): the bias step (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8)
-    const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
-    __half2 h0 = __halves2half2(one, one), h1 = __halves2half2(one, zero), hz = __halves2half2(zero, zero);
-    uint4 pk, pz;
-    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    pk.z = *reinterpret_cast<uint32_t*>(&hz); pk.w = pk.z;
-    pz.x = pz.y = pz.z = pz.w = pk.z;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      *reinterpret_cast<uint4*>(my_a + b * kABytes + KC * (128 * 16) + lt * 16) = pk;
-      *reinterpret_cast<uint4*>(my_a + b * kABytes + (KC + 1) * (128 * 16) + lt * 16) = pz;
-    }
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (tid == 0) {
-    mbar_expect_tx(mbar_b, kBBytes);
-    bulk_g2s(smem_u32(s_b), A.b_packed, kBBytes, mbar_b);
-  }
-  const uint32_t tmem_base = *s_tmem;
-  mbar_wait(mbar_b, 0);
-
-  float* my_stage = s_stage + (wg * 4 + ty) * WST;
-  const uint32_t a_addr = smem_u32(my_a), b_addr = smem_u32(s_b);
-  const uint32_t idesc = make_idesc(64);
-  const uint64_t ad0 = make_desc(a_addr, 128 * 16, 128), bd0 = make_desc(b_addr, N * 16, 128);
-  const uint32_t bar0 = smem_u32(s_mbar + wg * kBarsPerWg);
-  auto bar_full = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
-  auto bar_free = [&](int slot) { return bar0 + 8u * (uint32_t)(2 + slot); };
-  auto bar_aready = [&](int buf) { return bar0 + 8u * (uint32_t)(4 + buf); };
-  const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
-  const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
-
-  const long long tile_step = (long long)gridDim.x * kWG;
-  const long long first = (long long)blockIdx.x * kWG + wg;
-  const int n_my = first < A.total_tiles ? (int)((A.total_tiles - first + tile_step - 1) / tile_step) : 0;
-  const int total_jobs = n_my * NJ;
-
-  auto tile_xyf = [&](int i, int& x0, int& y0, int& f) {
-    const unsigned tile = (unsigned)(first + (long long)i * tile_step);   // total_tiles < 2^31 (checked by the host)
-    const unsigned q = tile / (unsigned)A.tiles_x;
-    x0 = (int)(tile - q * (unsigned)A.tiles_x) * kTileW;
-    const unsigned ff = q / (unsigned)A.tiles_y;
-    y0 = (int)(q - ff * (unsigned)A.tiles_y) * kTileH;
-    f = (int)ff;
-  };
-  // stage (asynchronously) the window rows this warp's 32 pixels tap, clamp-to-edge
-  auto prefetch = [&](int i) {
-    if (i < n_my) {
-      int x0, y0, f;
-      tile_xyf(i, x0, y0, f);
-      const int64_t src0 = (int64_t)f * A.in_sn;
-      for (int e = tx; e < SWP * HY; e += 32) {
-        const int sy = e / SWP, sx = e - sy * SWP;
-        const int gx = clampi(x0 + sx - OX, 0, A.w - 1), gy = clampi(y0 + ty + sy - OY, 0, A.h - 1);
-        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
-        if (A.io.in_fmt == MPVP_FMT_F32) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(my_stage + e)),
-                       "l"(static_cast<const float*>(A.in) + off)
-                       : "memory");
-        } else {
-          my_stage[e] = load_px(A.in, off, A.io.in_fmt, A.io.in_max);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  // im2col + normalisation of tile i -> A buffer i & 1; returns the pixel's (mean, stddev, centre sample)
-  auto build_a = [&](int i, float& mstd0, float& mstd1, float& orig) {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-    unsigned char* abuf = my_a + (i & 1) * kABytes;
-    float xs[K];
-    float sum = 0.f, sumsq = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int a = k / S, b = k % S;
-      const int dx = DIR == 0 ? a : b, dy = DIR == 0 ? b : a;
-      xs[k] = my_stage[dy * SWP + tx + dx];
-      sum += xs[k];
-      sumsq = fmaf(xs[k], xs[k], sumsq);
-    }
-    mstd0 = sum / (float)K;
-    mstd1 = sumsq / (float)K - mstd0 * mstd0;
-    const float mstd2 = mstd1 >= kEps ? rsqrtf(mstd1) : 0.0f;
-    mstd1 *= mstd2;
-    orig = xs[3 * S + (S / 2 - 1)];
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc) {
-      __half2 h[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        h[e] = __floats2half2_rn((xs[kc * 8 + 2 * e] - mstd0) * mstd2, (xs[kc * 8 + 2 * e + 1] - mstd0) * mstd2);
-      uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
-      pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
-      pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
-      pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-      *reinterpret_cast<uint4*>(abuf + kc * (128 * 16) + lt * 16) = pk;
-    }
-    fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
-    __syncwarp();         // the whole warp is done reading the staged window (the next prefetch overwrites it)
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_aready(i & 1)) : "memory");
-  };
-  // issuing thread only: refill slot job & 1 with the 64 accumulator columns of `job`
-  auto issue_job = [&](int job) {
-    const int i = job / NJ;
-    const int jb = job % NJ, slot = job & 1;
-    if (jb == 0) mbar_wait(bar_aready(i & 1), (uint32_t)((i >> 1) & 1));
-    if (job >= 2) mbar_wait(bar_free(slot), (uint32_t)(((job >> 1) - 1) & 1));
-    tc_fence_after();
-    // descriptors differ from the base ones only in the (address >> 4) field
-    const uint64_t ad = ad0 + (uint64_t)(((uint32_t)(i & 1) * kABytes) >> 4);
-    const uint64_t bd = bd0 + (uint64_t)((jb * 64 * 16) >> 4);
-#pragma unroll
-    for (int j = 0; j < KX / 16; ++j)
-      umma_f16(d_col + (uint32_t)(slot * 64), ad + (uint64_t)((j * 2 * (128 * 16)) >> 4), bd + (uint64_t)((j * 2 * (N * 16)) >> 4),
-               idesc, j > 0 ? 1u : 0u);
-    umma_commit(bar_full(slot));
-  };
-
-  if (n_my > 0) {
-    float m0c, m1c, origc, m0n = 0.f, m1n = 0.f, orign = 0.f;
-    prefetch(0);
-    build_a(0, m0c, m1c, origc);
-    prefetch(1);
-    if (issuer) {
-      issue_job(0);
-      issue_job(1);
-    }
-    // register staging: 16 columns = 8 neurons (8 logits, then their 8 elliott inputs), double-buffered
-    uint32_t va[16], vb[16];
-    mbar_wait(bar_full(0), 0);
-    tc_fence_after();
-    tmem_ld16_issue(d_lane, va);
-    tmem_ld_wait();
-
-    int job = 0;  // job whose columns are being consumed
-    float2 wsum2, vsum2;
-    // 8 neurons: packed f32x2, ONE Newton reciprocal for all 8 (common denominator u0 u1 u2 u3 per lane)
-    auto consume = [&](const uint32_t (&cur)[16]) {
-      float2 s1[4], u[4], pk[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        s1[k].x = ex2_approx(__uint_as_float(cur[2 * k]));
-        s1[k].y = ex2_approx(__uint_as_float(cur[2 * k + 1]));
-        const float2 t = make_float2(__uint_as_float(cur[8 + 2 * k]), __uint_as_float(cur[8 + 2 * k + 1]));
-        u[k].x = 1.0f + fabsf(t.x);
-        u[k].y = 1.0f + fabsf(t.y);
-        pk[k] = __fmul2_rn(s1[k], t);
-      }
-      const float2 n01 = __ffma2_rn(pk[1], u[0], __fmul2_rn(pk[0], u[1]));
-      const float2 n23 = __ffma2_rn(pk[3], u[2], __fmul2_rn(pk[2], u[3]));
-      const float2 d01 = __fmul2_rn(u[0], u[1]), d23 = __fmul2_rn(u[2], u[3]);
-      const float2 num = __ffma2_rn(n23, d01, __fmul2_rn(n01, d23));
-      const float2 den = __fmul2_rn(d01, d23);
-      float2 rn;  // ~ -1/den: bit-trick seed with the sign bit set, two Newton steps rn <- rn * (2 + den * rn)
-      rn.x = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(den.x));
-      rn.y = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(den.y));
-      rn = __fmul2_rn(rn, __ffma2_rn(den, rn, make_float2(2.f, 2.f)));
-      rn = __fmul2_rn(rn, __ffma2_rn(den, rn, make_float2(2.f, 2.f)));
-      vsum2 = __ffma2_rn(num, rn, vsum2);  // accumulates -vsum
-      wsum2 = __fadd2_rn(wsum2, __fadd2_rn(__fadd2_rn(s1[0], s1[1]), __fadd2_rn(s1[2], s1[3])));
-    };
-    // quarter Q of `job` (slot SLOT = job & 1) is in `cur`: fetch the next 16 columns into `nxt`, consume `cur`; when
-    // the last quarter has landed in registers the slot is handed back and (issuing thread) refilled with job + 2
-    auto step = [&](auto qtag, auto stag, const uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
-      constexpr int Q = decltype(qtag)::value, SLOT = decltype(stag)::value;
-      bool loading = true;
-      if constexpr (Q < 3) {
-        tmem_ld16_issue(d_lane + (uint32_t)(SLOT * 64 + (Q + 1) * 16), nxt);
-      } else {
-        loading = job + 1 < total_jobs;
-        if (loading) {
-          mbar_wait(bar_full(SLOT ^ 1), (uint32_t)(((job + 1) >> 1) & 1));
-          tc_fence_after();
-          tmem_ld16_issue(d_lane + (uint32_t)((SLOT ^ 1) * 64), nxt);
-        }
-      }
-      consume(cur);
-      if (loading) tmem_ld_wait();
-      if constexpr (Q == 2) {
-        tc_fence_before();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free(SLOT)) : "memory");
-        if (issuer && job + 2 < total_jobs) issue_job(job + 2);
-      }
-    };
-    using Q0 = std::integral_constant<int, 0>;
-    using Q1 = std::integral_constant<int, 1>;
-    using Q2 = std::integral_constant<int, 2>;
-    using Q3 = std::integral_constant<int, 3>;
-
-    for (int i = 0; i < n_my; ++i) {
-      wsum2 = make_float2(0.f, 0.f);
-      vsum2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-      for (int jb = 0; jb < NJ; jb += 2) {   // NJ is even: slots alternate 0, 1 at compile time
-        step(Q0{}, Q0{}, va, vb);
-        step(Q1{}, Q0{}, vb, va);
-        step(Q2{}, Q0{}, va, vb);
-        step(Q3{}, Q0{}, vb, va);
-        ++job;
-        step(Q0{}, Q1{}, va, vb);
-        step(Q1{}, Q1{}, vb, va);
-        step(Q2{}, Q1{}, va, vb);
-        step(Q3{}, Q1{}, vb, va);
-        ++job;
-        if (jb == 0 && i + 1 < n_my) {
-          build_a(i + 1, m0n, m1n, orign);
-          prefetch(i + 2);
-        }
-      }
-      int x0, y0, f;
-      tile_xyf(i, x0, y0, f);
-      const int x = x0 + tx, y = y0 + ty;
-      if (x < A.w && y < A.h) {
-        const float wsum = wsum2.x + wsum2.y, vsum = -(vsum2.x + vsum2.y);
-        const float pred = fminf(fmaxf(m0c + 5.0f * vsum / wsum * m1c, 0.f), 1.f);
-        const int64_t o = (int64_t)f * A.out_sn;
-        if (DIR == 0) {
-          store_px(A.out, o + (int64_t)(2 * y) * A.out_sy + x, origc, A.io.out_fmt, A.io.out_max);
-          store_px(A.out, o + (int64_t)(2 * y + 1) * A.out_sy + x, pred, A.io.out_fmt, A.io.out_max);
-        } else {
-          store_px2(A.out, o + (int64_t)y * A.out_sy + 2 * x, origc, pred, A.io.out_fmt, A.io.out_max);
-        }
-      }
-      m0c = m0n; m1c = m1n; origc = orign;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // Epilogue variants (A/B switch MPVP_NNEDI3_EPI): 0 = reciprocal on the MUFU pipe, 1 = scalar Newton
 // reciprocal on the FMA pipe, 2 = Newton in packed f32x2 arithmetic (two neurons per instruction), 3 (default) =
 // packed, with one Newton reciprocal shared by 8 neurons (common denominator).
@@ -798,52 +503,9 @@ static int epi_mode() {
   return v;
 }
 
-// MPVP_NNEDI3_PIPE=1 selects the mbarrier-pipelined kernel for nns128/256 (experiment, read at weight upload).
-// Measured on nns256-win8x6 2160p x2: 6.43 ms vs 5.33 ms for the barrier-synchronised kernel -- the two-slot ring
-// removes every bar.sync but its N = 64 MMAs re-read A twice as often, the x16 staging doubles the TMEM load /
-// wait count and the spinning mbarrier waits take issue slots from the working warps (3330 vs 2150 warp
-// instructions per 32 pixels).  Kept as the starting point for a producer-warp (setmaxnreg) version.
-static bool pipe_enabled() {
-  static const bool v = [] {
-    const char* e = getenv("MPVP_NNEDI3_PIPE");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
-template <int S, int DIR, int NNS>
-int launch_tc_pipe(const NnTcArgs& a0, int device, cudaStream_t stream) {
-  constexpr int K = 8 * S, KX = K + 16, N = 2 * NNS;
-  constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
-  constexpr int SWP = kTileW + HX - 1, WST = (SWP * HY + 3) & ~3;
-  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * 2 * KX * 128 * 2 + sizeof(float) * kWG * 4 * WST + 8 * (kWG * 6 + 1) + 16;
-  if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the kernel allocates all 512 TMEM columns
-  NnTcArgs a = a0;
-  a.tiles_x = (a.w + kTileW - 1) / kTileW;
-  a.tiles_y = (a.h + kTileH - 1) / kTileH;
-  a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
-  MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
-  auto kern = nnedi3_tc_pipe_kernel<S, DIR, NNS>;
-  MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long grid = sm_count(device);
-  const long long need = (a.total_tiles + kWG - 1) / kWG;
-  if (grid > need) grid = need;
-  if (grid < 1) return MPVP_OK;
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MPVP_CUDA_OK(cudaGetLastError());
-  return MPVP_OK;
-}
-
 template <int S, int DIR, int NNS>
 int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
-  if constexpr (NNS >= 128) {
-    if (a0.group == 8) return launch_tc_pipe<S, DIR, NNS>(a0, device, stream);
-  }
-  if (a0.group != 16) {
-    set_error("NNEDI3 weights were packed for the pipelined kernel (MPVP_NNEDI3_PIPE changed after upload?)");
-    return MPVP_E_INVALID;
-  }
+  MPVP_REQUIRE(a0.group == 16, "NNEDI3 weights were packed with %d neurons per accumulator block, the kernel expects 16", a0.group);
   constexpr int K = 8 * S, KX = K + 16, N = 2 * NNS;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
@@ -866,6 +528,7 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   long long grid = sm_count(device);
   const long long need = (a.total_tiles + kWG - 1) / kWG;
   if (grid > need) grid = need;
+  grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
   kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -888,8 +551,8 @@ int dispatch_nns(const NnTcArgs& a, int nns, int device, cudaStream_t st) {
 
 }  // namespace
 
-// B row order the kernels expect for a given nns: the pipelined kernel (nns >= 128) stages 16 columns at a time
-int nnedi3_group_size(int nns) { return (nns >= 128 && pipe_enabled()) ? 8 : 16; }
+// B row order the kernel expects: blocks of 32 accumulator columns = 16 neurons (16 logits, then their 16 elliott inputs)
+int nnedi3_group_size(int) { return 16; }
 
 int nnedi3_tc(const mpvp_weights* nn, int direction, const void* in, void* out, int n, int h, int w,
               int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n, int64_t out_stride_y, const IoFmt& io,

@@ -280,6 +280,7 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   }
   long long grid = (long long)sm_count(device) * per_sm;
   if (grid > a.total_tiles) grid = a.total_tiles;
+  grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
   kern<<<(unsigned)grid, NT, smem, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -331,6 +332,7 @@ extern "C" int mpvp_ravu_launch_io(const mpvp_weights* lut, const mpvp_key_param
                lut->lut_h, (taps / 2 + 3) / 4);
   MPVP_REQUIRE(key->n_gauss == g * g && key->n_strength == 9 && key->n_strength_thr == 0,
                "key params do not describe a RAVU (log2-strength) hook");
+  if (int rck = check_fast_key(key)) return rck;
   MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 && (out_stride_c % 2) == 0 &&
                    (reinterpret_cast<uintptr_t>(out) % (2 * fmt_bytes(iof.out_fmt))) == 0,
                "output rows must be aligned to a pixel pair (even strides, base aligned to two elements)");

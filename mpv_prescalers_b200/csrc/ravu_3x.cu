@@ -24,6 +24,9 @@ extern "C" int mpvp_ravu3x_launch_io(const mpvp_weights* lut, const mpvp_key_par
   if (rc) return rc;
   MPVP_REQUIRE(key->n_strength == 3 && key->n_strength_thr == 2, "ravu-3x expects 2 strength thresholds");
   MPVP_REQUIRE(key_mode >= 0 && key_mode <= 2, "key_mode %d", key_mode);
+  if (!exact_key()) {
+    if (int rck = check_fast_key(key)) return rck;
+  }
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);

@@ -22,6 +22,9 @@ extern "C" int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_
   int rc = check_common(lut, key, radius, in, out, n, h, w, (taps + 1) / 2, 288, g * g);
   if (rc) return rc;
   MPVP_REQUIRE(key->n_strength == 4 && key->n_strength_thr == 3, "ravu-lite expects 3 strength thresholds");
+  if (!exact_key()) {
+    if (int rck = check_fast_key(key)) return rck;
+  }
   MPVP_REQUIRE((out_stride_y % 2) == 0 && (out_stride_n % 2) == 0 &&
                    (reinterpret_cast<uintptr_t>(out) % (2 * fmt_bytes(iof.out_fmt))) == 0,
                "output rows must be aligned to a pixel pair (even strides, base aligned to two elements)");

@@ -564,6 +564,7 @@ int launch_lite_impl(const LiteArgs& a0, int device, cudaStream_t stream) {
   }
   long long grid = (long long)sm_count(device) * per_sm;
   if (grid > a.total_tiles) grid = a.total_tiles;
+  grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
   kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, tmap);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -1,22 +1,51 @@
-// RAVU-Zoom(-AR): arbitrary-ratio upscale, one thread per OUTPUT pixel.
+// RAVU-Zoom(-AR): arbitrary-ratio upscale.
 //
 //   RAVU-Zoom      ravu-zoom-r2.hook:15-134, ravu-zoom-r3.hook:15-180
 //   RAVU-Zoom-AR   ravu-zoom-ar-r2.hook:15-208  (3-channel mat4x3 form: ravu-zoom-ar-r2-rgb.hook:153-223)
 //
-// Position arithmetic follows SURVEY.md App. D.6 exactly (pos = ((o + 0.5) / O) * I in fp32, then
-// subpix = fract(pos - 0.5)): at integer ratios a 1-ulp difference moves the 4x4 / 6x6 window.
-// A CTA owns a 32x8 tile of output pixels; the source rectangle it taps (at most tile + 2r + 2,
-// because the hook only runs when upscaling) is staged in shared memory with clamp-to-edge.  The LUT
-// ([288*9][B*9] float4, FILTER LINEAR) stays in global memory / L2 and is fetched with an explicit
-// fp32 bilinear blend of four texels, at the same texel coordinates the GL sampler would use.
+// What the shader does per OUTPUT pixel: pos = HOOKED_pos * HOOKED_size; subpix = fract(pos - 0.5); window of (2r)^2 source
+// texels around floor(pos - 0.5); key -> LUT row; weights = LINEAR-filtered fetches of a [288*9][B*9] LUT at
+// (blk/B + LUTPOS(subpix.x)/B, row/288 + LUTPOS(subpix.y)/288) for the first half of the taps and at the mirrored
+// sub-pixel position for the second half (ravu-zoom-r3.hook:23-31,128-177).
+//
+// Two device paths, same arithmetic contract:
+//
+//  * PHASE path (rational ratios with few sub-pixel phases: 2x, 3x, 3/2, 4/3 ...).  The sub-pixel phase of an output
+//    column / row takes only a handful of values (up to fp32 rounding of `pos`), so the bilinear LUT blend is done ONCE
+//    per (phase class pair, LUT row, tap) by a setup kernel into a phase LUT (cached per geometry on the weight handle)
+//    instead of 10 four-texel gathers per output pixel.  Launch = a key pre-pass (one key per SOURCE cell -> uint16 map;
+//    every output pixel whose floor(pos - 0.5) coincides shares window and bucket) + a convolution kernel whose
+//    persistent CTAs each own a contiguous run of (class pair, member tile) work items with the class pair's phase LUT
+//    ([288][taps] float32) resident in shared memory -- the structure of the RAVU-Lite / RAVU-3x kernels.
+//  * GENERAL path (any ratio): one thread per output pixel, explicit fp32 blend of the four LUT texels.
+//
+// Position arithmetic follows SURVEY.md App. D.6 exactly (pos = ((o + 0.5) / O) * I in fp32, then subpix = fract(pos - 0.5)):
+// at integer ratios a 1-ulp difference moves the window.  The LUT coordinate arithmetic also follows the shader's fp32
+// operation order (coordinate = blk/B + LUTPOS/B resp. row/288 + LUTPOS/288, then * texture size - 0.5 as the LINEAR
+// sampler does): the anti-ringing soft-min/max raises tap values to the 32nd power, which makes its result hypersensitive
+// to blend weights that are exactly zero in the reference (a 3e-8 weight on a tap 2x brighter than the rest moves the
+// clamp bound by 1e-2), so "equal up to rounding" is not good enough there.
+// The texture-unit fetch (8-bit blend weights, what a GL driver does) is kept behind MPVP_ZOOM_TEX=1 only: measured
+// 1.16e-3 max abs error against the oracle on a 1280x720 -> 3840x2160 frame, outside the 1e-3 parity bound.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
 namespace mpvp {
 namespace {
+
+struct ClassPair {
+  int xsoff, ysoff;            // first x / y member segment of the two classes in the plan's segment arrays
+  int tiles_x, tiles_y;        // member tiles per frame = segments of the x class  x  segments of the y class
+  int tile_start;              // first work item of this class pair (work items are class-pair major)
+  int pad;
+};
 
 struct ZoomArgs {
   const void* __restrict__ in;   // planes of format io.in_fmt
@@ -32,12 +61,18 @@ struct ZoomArgs {
   long long total_tiles;
   float ar_strength;
   mpvp_key_params key;
+  // phase path
+  const int* __restrict__ xo; const int* __restrict__ xb;   // output coordinate / base texel of every class member
+  const int* __restrict__ yo; const int* __restrict__ yb;
+  const int2* __restrict__ xseg; const int2* __restrict__ yseg;   // member segments (first member, count): one tile side each
+  const ClassPair* __restrict__ cps;
+  int ncp;
+  const float* __restrict__ plut;   // [ncp][288][PL]
+  unsigned short* __restrict__ kmap;  // [n][h + 1][w + 1] LUT row of the source cell with base texel (x - 1, y - 1)
+  int sw, sh;                       // staged source rectangle (pitch, rows) the plan needs
 };
 
-#ifndef MPVP_X_ZOOM_MANUAL
-#define MPVP_X_ZOOM_MANUAL 0
-#endif
-constexpr int kTOW = 32, kTOH = 32, kNT = 256;  // output tile; each thread owns one column and kTOH/8 rows
+constexpr int kTOW = 32, kTOH = 32, kNT = 256;  // general path: output tile; each thread owns one column and kTOH/8 rows
 
 // Canonical position arithmetic: base texel index and sub-pixel phase of output coordinate o.
 __device__ __forceinline__ void zoom_pos(int o, int O, int I, int& base, float& sub) {
@@ -46,39 +81,39 @@ __device__ __forceinline__ void zoom_pos(int o, int O, int I, int& base, float& 
   sub = __fsub_rn(t, floorf(t));
   base = (int)floorf(__fsub_rn(pos, sub));
 }
+// the same on the host (x86-64 SSE arithmetic is IEEE fp32 op by op; volatile keeps every rounding)
+void zoom_pos_host(int o, int O, int I, int& base, float& sub) {
+  volatile float a = (float)o + 0.5f;
+  volatile float q = a / (float)O;
+  volatile float pos = q * (float)I;
+  volatile float t = pos - 0.5f;
+  volatile float fl = floorf(t);
+  volatile float s = t - fl;
+  volatile float d = pos - s;
+  sub = s;
+  base = (int)floorf(d);
+}
 
-// LUTPOS(x, 9) = mix(0.5/9, 1 - 0.5/9, x) = a*(1-x) + b*x
+// LUTPOS(x, 9) = mix(0.5/9, 1 - 0.5/9, x) = a*(1-x) + b*x   (ravu-zoom-r2.hook:23)
 __device__ __forceinline__ float lutpos9(float x) {
   const float a = __fdiv_rn(0.5f, 9.0f);
   const float b = __fsub_rn(1.0f, a);
   return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, x)), __fmul_rn(b, x));
 }
 
-// Per output column (or row): everything that depends on one coordinate only.  The GL LINEAR fetch at
-// normalised coordinate c of an axis with `size` texels reads texels floor(c*size - 0.5) and +1 with weight
-// frac(c*size - 0.5); inside a 9-texel LUT block that is i0 = floor(8 s) and f = frac(8 s) for the direct
-// half of the taps (sub-pixel phase s) and the same at 1 - s for the mirrored half (ravu-zoom-r2.hook:24-31).
-struct AxisEntry {
-  int base;        // source texel index of window tap 0 minus the tile origin (filled by the caller)
-  int i0, i0m;     // first LUT texel inside the 9-texel block: direct / mirrored
-  float f, fm;     // blend weight of texel i0+1: direct / mirrored
-  float u, um;     // the same as continuous texel coordinates inside the block (texel centres at k + 0.5)
-};
+// The LINEAR sampler at normalised coordinate c of an axis with `size` texels: texel index floor(c*size - 0.5) and the
+// blend weight of its successor, in fp32 exactly as the shader + sampler arithmetic of the oracle evaluates them.
+__device__ __forceinline__ void lin_coord(float c, int size, int& i0, float& f) {
+  const float u = __fsub_rn(__fmul_rn(c, (float)size), 0.5f);
+  const float u0 = floorf(u);
+  i0 = (int)u0;
+  f = __fsub_rn(u, u0);
+}
 
-__device__ __forceinline__ AxisEntry axis_entry(int o, int O, int I, int groups) {
-  // groups = number of 9-texel blocks along this LUT axis (B for x, 288 rows for y)
-  AxisEntry e;
-  float sub;
-  zoom_pos(o, O, I, e.base, sub);
-  const float p = lutpos9(sub), ip = __fsub_rn(1.0f, p);
-  // the shader divides by `groups` to normalise and the sampler multiplies by groups*9 again
-  const float u = __fsub_rn(__fmul_rn(__fdiv_rn(p, (float)groups), (float)(groups * 9)), 0.5f);
-  const float um = __fsub_rn(__fmul_rn(__fdiv_rn(ip, (float)groups), (float)(groups * 9)), 0.5f);
-  const float u0 = floorf(u), um0 = floorf(um);
-  e.i0 = (int)u0; e.f = __fsub_rn(u, u0);
-  e.i0m = (int)um0; e.fm = __fsub_rn(um, um0);
-  e.u = u + 0.5f; e.um = um + 0.5f;
-  return e;
+// block offset literal of the shader: vec2(0.2, coord_y) etc. = float(blk / B)
+template <int B>
+__device__ __forceinline__ float blk_off(int blk) {
+  return (float)((double)blk / (double)B);
 }
 
 // one LUT texel as float4, from fp32 or binary16 storage
@@ -94,9 +129,23 @@ __device__ __forceinline__ float4 lut_texel(const void* __restrict__ lut, int id
   }
 }
 
-// TEXF: the LUT fetch is ONE texture instruction (hardware bilinear blend of the four binary16 texels, exactly what
-// the reference's FILTER LINEAR sampler does, 8-bit blend weights: |error| <= 9e-5) instead of
-// four gathered loads and twelve FMAs.
+// two-stage lerp of the sampler: (t00 (1-fu) + t10 fu) (1-fv) + (t01 (1-fu) + t11 fu) fv
+__device__ __forceinline__ float lerp2(float t00, float t10, float t01, float t11, float fu, float fv) {
+  const float gu = __fsub_rn(1.0f, fu), gv = __fsub_rn(1.0f, fv);
+  const float top = __fadd_rn(__fmul_rn(t00, gu), __fmul_rn(t10, fu));
+  const float bot = __fadd_rn(__fmul_rn(t01, gu), __fmul_rn(t11, fu));
+  return __fadd_rn(__fmul_rn(top, gv), __fmul_rn(bot, fv));
+}
+
+__device__ __forceinline__ float key_luma709(float r, float g, float b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(r, 0.2126f), __fmul_rn(g, 0.7152f)), __fmul_rn(b, 0.0722f));
+}
+
+// =====================================================================================================================
+// GENERAL path: one thread per output pixel
+// =====================================================================================================================
+// TEXF (opt-in): the LUT fetch is ONE texture instruction (hardware bilinear blend of the four binary16 texels with 8-bit
+// blend weights) instead of four gathered loads and the fp32 blend.
 template <int R, int C, int KEYMODE, bool AR, bool LUTH, bool TEXF>
 __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ ZoomArgs A) {
   constexpr int N = 2 * R, TAPS = N * N, G = 4;
@@ -110,7 +159,10 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
 
   __shared__ float s_src[NP * PLANE];
   __shared__ int s_key[CW * CH];
-  __shared__ AxisEntry s_ax[kTOW], s_ay[kTOH];
+  __shared__ int s_bx[kTOW], s_by[kTOH];               // base texel - first base of the tile
+  __shared__ int s_xi[kTOW][2 * B];                    // LUT texel column of (mirrored, blk)
+  __shared__ float s_xf[kTOW][2 * B];                  // blend weight of its successor
+  __shared__ float s_spy[kTOH][2];                     // LUTPOS(subpix.y) / 288: direct, mirrored
 
   const int tid = threadIdx.x;
   static_assert(kTOW == 32 && kTOH == 32 && kNT == 256, "the patch mapping below assumes 32x32 tiles and 8 warps");
@@ -133,13 +185,31 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     __syncthreads();
     // ---- per-axis tables -------------------------------------------------------------------------
     if (tid < kTOW) {
-      AxisEntry e = axis_entry(min(ox0 + tid, A.ow - 1), A.ow, A.w, B);
-      e.base -= bx_first;
-      s_ax[tid] = e;
+      int base;
+      float sub;
+      zoom_pos(min(ox0 + tid, A.ow - 1), A.ow, A.w, base, sub);
+      s_bx[tid] = base - bx_first;
+      const float p = lutpos9(sub), ip = __fsub_rn(1.0f, p);
+      const float sp[2] = {__fdiv_rn(p, (float)B), __fdiv_rn(ip, (float)B)};
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int blk = 0; blk < B; ++blk) {
+          int i0;
+          float fr;
+          lin_coord(__fadd_rn(blk_off<B>(blk), sp[m]), LWt, i0, fr);
+          s_xi[tid][m * B + blk] = i0;
+          s_xf[tid][m * B + blk] = fr;
+        }
     } else if (tid < kTOW + kTOH) {
-      AxisEntry e = axis_entry(min(oy0 + tid - kTOW, A.oh - 1), A.oh, A.h, 288);
-      e.base -= by_first;
-      s_ay[tid - kTOW] = e;
+      const int j = tid - kTOW;
+      int base;
+      float sub;
+      zoom_pos(min(oy0 + j, A.oh - 1), A.oh, A.h, base, sub);
+      s_by[j] = base - by_first;
+      const float p = lutpos9(sub), ip = __fsub_rn(1.0f, p);
+      s_spy[j][0] = __fdiv_rn(p, 288.0f);
+      s_spy[j][1] = __fdiv_rn(ip, 288.0f);
     }
     // ---- stage the source rectangle (clamp-to-edge) ------------------------------------------------
     const int need_w = ncx + N - 1, need_h = ncy + N - 1;
@@ -156,7 +226,7 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
           const float c0 = load_px_t<FMT>(A.in, off, A.io.in_max);
           const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
           const float c2 = load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max);
-          s_src[d] = (KEYMODE == 2) ? __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2126f), __fmul_rn(c1, 0.7152f)), __fmul_rn(c2, 0.0722f)) : c0;
+          s_src[d] = (KEYMODE == 2) ? key_luma709(c0, c1, c2) : c0;
           s_src[PLANE + d] = c0;
           s_src[2 * PLANE + d] = c1;
           s_src[3 * PLANE + d] = c2;
@@ -175,20 +245,19 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
     }
     __syncthreads();
 
-    // A warp covers an 8x4 patch of output pixels, not a 32x1 row segment: the LUT fetch is bound by the number of
-    // distinct texel neighbourhoods per texture instruction, and a compact patch spans 3-4 times fewer source cells
-    // (hence LUT row groups) than a row segment does.
+    // A warp covers an 8x4 patch of output pixels, not a 32x1 row segment: a compact patch spans 3-4 times fewer
+    // source cells (hence LUT row groups) than a row segment does.
 #pragma unroll 1
     for (int rr = 0; rr < RPT; ++rr) {
       const int patch = rr * (kNT / 32) + (tid >> 5);           // 4 patches across, 8 down
       const int lx = (patch & 3) * 8 + (tid & 7), ly = (patch >> 2) * 4 + ((tid >> 3) & 3);
       const int ox = ox0 + lx, oy = oy0 + ly;
       if (ox >= A.ow || oy >= A.oh) continue;
-      const AxisEntry ex = s_ax[lx];
-      const AxisEntry ey = s_ay[ly];
-      const int row = s_key[ey.base * CW + ex.base];
+      const int cbx = s_bx[lx], cby = s_by[ly];
+      const int row = s_key[cby * CW + cbx];
       if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
-      const float* __restrict__ kb = s_src + ey.base * SWt + ex.base;  // window tap (0,0)
+      const float* __restrict__ kb = s_src + cby * SWt + cbx;  // window tap (0,0)
+      const float coord_y = __fdiv_rn((float)row, 288.0f);
 
       float res[C];
       float hi[C], lo[C], hi2[C], lo2[C];
@@ -197,31 +266,30 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
 
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        // LUT rows: row*9 + i0 (+1), clamp-to-edge on the whole texture like the GL sampler
-        const int yi = row * 9 + (m ? ey.i0m : ey.i0);
+        // LUT rows: clamp-to-edge on the whole texture like the GL sampler
+        int yi;
+        float fv;
+        lin_coord(__fadd_rn(coord_y, s_spy[ly][m]), LHt, yi, fv);
         const int y0 = clampi(yi, 0, LHt - 1), y1 = clampi(yi + 1, 0, LHt - 1);
-        const float fv = m ? ey.fm : ey.f, fu = m ? ex.fm : ex.f;
-        const float w00 = (1.0f - fu) * (1.0f - fv), w10 = fu * (1.0f - fv), w01 = (1.0f - fu) * fv, w11 = fu * fv;
-        const int xi = m ? ex.i0m : ex.i0;
 #pragma unroll
         for (int blk = 0; blk < B; ++blk) {
-          const int x0 = clampi(blk * 9 + xi, 0, LWt - 1), x1 = clampi(blk * 9 + xi + 1, 0, LWt - 1);
+          const int xi = s_xi[lx][m * B + blk];
+          const float fu = s_xf[lx][m * B + blk];
+          const int x0 = clampi(xi, 0, LWt - 1), x1 = clampi(xi + 1, 0, LWt - 1);
           auto fetch = [&](const void* __restrict__ lut) {
             const float4 t00 = lut_texel<LUTH>(lut, y0 * LWt + x0), t10 = lut_texel<LUTH>(lut, y0 * LWt + x1);
             const float4 t01 = lut_texel<LUTH>(lut, y1 * LWt + x0), t11 = lut_texel<LUTH>(lut, y1 * LWt + x1);
             float4 r;
-            r.x = t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-            r.y = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-            r.z = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-            r.w = t00.w * w00 + t10.w * w10 + t01.w * w01 + t11.w * w11;
+            r.x = lerp2(t00.x, t10.x, t01.x, t11.x, fu, fv);
+            r.y = lerp2(t00.y, t10.y, t01.y, t11.y, fu, fv);
+            r.z = lerp2(t00.z, t10.z, t01.z, t11.z, fu, fv);
+            r.w = lerp2(t00.w, t10.w, t01.w, t11.w, fu, fv);
             return r;
           };
           float4 w4;
           float av[4] = {0.f, 0.f, 0.f, 0.f};
-          // MPVP_X_ZOOM_MANUAL of the B blocks are fetched by explicit loads + fp32 blend even on the texture path, to
-          // take load off the texture data pipe (the binding unit)
-          if (TEXF && blk >= MPVP_X_ZOOM_MANUAL) {
-            const float X = (float)(blk * 9) + (m ? ex.um : ex.u), Y = (float)(row * 9) + (m ? ey.um : ey.u);
+          if constexpr (TEXF) {
+            const float X = (float)xi + fu + 0.5f, Y = (float)yi + fv + 0.5f;
             w4 = tex2D<float4>(A.tex, X, Y);
             if constexpr (AR) {
               const float4 a4 = tex2D<float4>(A.tex_ar, X, Y);
@@ -287,6 +355,7 @@ int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sm_count(device) * per_sm;
   if (grid > a.total_tiles) grid = a.total_tiles;
+  grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
   kern<<<(unsigned)grid, kNT, 0, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -294,16 +363,544 @@ int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   return MPVP_OK;
 }
 
+bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] != '0';
+}
+
 template <int R, int C, int KEYMODE, bool AR>
-int launch_zoom(const ZoomArgs& a, int device, cudaStream_t stream, bool half_lut) {
-  // MPVP_ZOOM_TEX=0: explicit fp32 blend of four loaded texels instead of the texture unit (A/B switch)
-  static const bool tex_ok = [] {
-    const char* e = getenv("MPVP_ZOOM_TEX");
-    return !(e && e[0] == '0');
-  }();
-  if (half_lut && tex_ok && a.tex && (!AR || a.tex_ar)) return launch_zoom_impl<R, C, KEYMODE, AR, true, true>(a, device, stream);
+int launch_zoom_general(const ZoomArgs& a, int device, cudaStream_t stream, bool half_lut) {
+  // MPVP_ZOOM_TEX=1: the texture unit does the bilinear blend (8-bit weights: outside the 1e-3 parity bound, opt-in only)
+  if (half_lut && env_flag("MPVP_ZOOM_TEX", false) && a.tex && (!AR || a.tex_ar))
+    return launch_zoom_impl<R, C, KEYMODE, AR, true, true>(a, device, stream);
   if (half_lut) return launch_zoom_impl<R, C, KEYMODE, AR, true, false>(a, device, stream);
   return launch_zoom_impl<R, C, KEYMODE, AR, false, false>(a, device, stream);
+}
+
+// =====================================================================================================================
+// PHASE path
+// =====================================================================================================================
+constexpr int kPTW = 64, kPTH = 16, kPNT = 256;   // member tile (64 x 16 output pixels of one class pair), threads
+constexpr int kMaxClasses = 8;                    // per axis
+constexpr int kMaxStep = 3;                       // base-texel distance of neighbouring class members
+constexpr float kClusterGap = 2.5e-4f;            // sub-pixel phases closer than this belong to one class ...
+constexpr float kMaxSpread = 2.6e-4f;             // ... whose total spread must stay below this (fp32 noise of `pos`)
+
+// ---- key pre-pass: LUT row of every source cell (base texel (x-1, y-1), x in [0, w], y in [0, h]) -------------------
+constexpr int kKTW = 64, kKTH = 16;
+template <int R, int C, int KEYMODE>
+__global__ void __launch_bounds__(256) zoom_key_kernel(const __grid_constant__ ZoomArgs A) {
+  constexpr int N = 2 * R, TAPS = N * N, G = 4;
+  constexpr int SW = kKTW + N - 1, SH = kKTH + N - 1;
+  __shared__ float s_k[SW * SH];
+  const int tid = threadIdx.x;
+  const int cw = A.w + 1, ch = A.h + 1;
+  TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next()) {
+    const int f = walk.f;
+    const int cx0 = walk.tix * kKTW, cy0 = walk.tiy * kKTH;   // cell tile origin (cell index = base + 1)
+    const int64_t src0 = (int64_t)f * A.in_sn;
+    __syncthreads();
+    dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
+      constexpr int FMT = decltype(ftag)::value;
+      for (int i = tid; i < SW * SH; i += 256) {
+        const int sy = i / SW, sx = i - sy * SW;
+        // window tap (0, 0) of cell (cx, cy) is source texel (cx - 1 - (R-1), cy - 1 - (R-1))
+        const int gx = clampi(cx0 - R + sx, 0, A.w - 1), gy = clampi(cy0 - R + sy, 0, A.h - 1);
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        if constexpr (C == 1) {
+          s_k[i] = load_px_t<FMT>(A.in, off, A.io.in_max);
+        } else if constexpr (KEYMODE == 2) {
+          s_k[i] = key_luma709(load_px_t<FMT>(A.in, off, A.io.in_max), load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max),
+                               load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max));
+        } else {
+          s_k[i] = load_px_t<FMT>(A.in, off, A.io.in_max);
+        }
+      }
+    });
+    __syncthreads();
+    for (int i = tid; i < kKTW * kKTH; i += 256) {
+      const int ly = i / kKTW, lx = i - ly * kKTW;
+      const int cx = cx0 + lx, cy = cy0 + ly;
+      if (cx >= cw || cy >= ch) continue;
+      const float* __restrict__ kb = s_k + ly * SW + lx;
+      float ks[TAPS];
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) ks[t] = kb[(t % N) * SW + (t / N)];
+      const int row = ravu_key2<STENCIL_RAVU, N, G, 3, true>(A.key, [&](int ii, int jj) { return ks[ii * N + jj]; });
+      A.kmap[((int64_t)f * ch + cy) * cw + cx] = (unsigned short)row;
+    }
+  }
+}
+
+// ---- phase LUT builder: plut[cp][row][t] = the sampler's blend at the class pair's representative sub-pixel phase ----
+struct BuildArgs {
+  const float* lut;      // [2592][LWt][4] float32 texels (already rounded to binary16 precision under the rgba16f policy)
+  const float* lut_ar;   // or null
+  const float* rep_x;    // [ncx] representative sub-pixel phase of every x class
+  const float* rep_y;    // [ncy]
+  float* plut;           // [ncy * ncx][288][PL]
+  int ncx, ncy;
+};
+template <int R, bool AR>
+__global__ void zoom_build_plut_kernel(const BuildArgs A) {
+  constexpr int N = 2 * R, TAPS = N * N;
+  constexpr int B = (TAPS / 2 + 3) / 4, LWt = B * 9, LHt = 288 * 9;
+  constexpr int PL = TAPS * (AR ? 2 : 1);
+  const int cp = blockIdx.y, row = blockIdx.x;
+  const int cx = cp % A.ncx, cy = cp / A.ncx;
+  for (int t = threadIdx.x; t < TAPS; t += blockDim.x) {
+    const bool m = t >= TAPS / 2;
+    const int k = m ? TAPS - 1 - t : t;
+    const int blk = k / 4, comp = k % 4;
+    const float px = lutpos9(A.rep_x[cx]), py = lutpos9(A.rep_y[cy]);
+    const float spx = __fdiv_rn(m ? __fsub_rn(1.0f, px) : px, (float)B);
+    const float spy = __fdiv_rn(m ? __fsub_rn(1.0f, py) : py, 288.0f);
+    int xi, yi;
+    float fu, fv;
+    lin_coord(__fadd_rn(blk_off<B>(blk), spx), LWt, xi, fu);
+    lin_coord(__fadd_rn(__fdiv_rn((float)row, 288.0f), spy), LHt, yi, fv);
+    const int x0 = clampi(xi, 0, LWt - 1), x1 = clampi(xi + 1, 0, LWt - 1);
+    const int y0 = clampi(yi, 0, LHt - 1), y1 = clampi(yi + 1, 0, LHt - 1);
+    auto blend = [&](const float* __restrict__ lut) {
+      return lerp2(lut[((size_t)y0 * LWt + x0) * 4 + comp], lut[((size_t)y0 * LWt + x1) * 4 + comp],
+                   lut[((size_t)y1 * LWt + x0) * 4 + comp], lut[((size_t)y1 * LWt + x1) * 4 + comp], fu, fv);
+    };
+    float* dst = A.plut + ((size_t)cp * 288 + row) * PL;
+    dst[t] = blend(A.lut);
+    if constexpr (AR) dst[TAPS + t] = blend(A.lut_ar);
+  }
+}
+
+// ---- convolution of one class pair's members ------------------------------------------------------------------------
+// PITCH: floats per phase-LUT row in shared memory, a multiple of 4 (16-byte weight loads) chosen so that PITCH / 4 is odd:
+// the 32 lanes of a warp gather 32 different rows, an odd 16-byte pitch spreads them over all bank groups.
+template <int R, bool AR>
+struct PhaseGeom {
+  static constexpr int TAPS = 4 * R * R;
+  static constexpr int PL = TAPS * (AR ? 2 : 1);
+  static constexpr int PITCH = ((PL / 4) | 1) * 4;
+};
+
+template <int R, int C, bool AR>
+__global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant__ ZoomArgs A) {
+  constexpr int N = 2 * R, TAPS = N * N;
+  constexpr int PL = PhaseGeom<R, AR>::PL, PITCH = PhaseGeom<R, AR>::PITCH;
+  constexpr bool POWT = AR && C == 1;   // anti-ringing powers once per staged source pixel (luma); 3-channel: on the fly
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_lut = reinterpret_cast<float*>(smem_raw);            // [288][PITCH]
+  float* s_src = s_lut + 288 * PITCH;                           // [C][sh][sw]
+  float4* s_pow = reinterpret_cast<float4*>(s_src + (((size_t)C * A.sh * A.sw + 3) & ~(size_t)3));   // [sh][sw] (POWT)
+  __shared__ int s_mxo[kPTW], s_mxb[kPTW], s_myo[kPTH], s_myb[kPTH];
+
+  const int tid = threadIdx.x;
+  const int SW = A.sw, PLANE = A.sw * A.sh;
+  const int cw = A.w + 1, ch = A.h + 1;
+  // contiguous run of work items (class-pair major): at most a couple of phase-LUT reloads per CTA
+  const long long T = A.total_tiles;
+  const long long w_begin = T * blockIdx.x / gridDim.x, w_end = T * (blockIdx.x + 1) / gridDim.x;
+  int cur_cp = -1;
+  int cpi = 0;
+  for (long long item = w_begin; item < w_end; ++item) {
+    while (cpi + 1 < A.ncp && item >= (long long)A.cps[cpi + 1].tile_start) ++cpi;
+    const ClassPair cp = A.cps[cpi];
+    const int local = (int)(item - cp.tile_start);
+    const int per_frame = cp.tiles_x * cp.tiles_y;
+    const int f = local / per_frame;
+    const int tl = local - f * per_frame;
+    const int tiy = tl / cp.tiles_x, tix = tl - tiy * cp.tiles_x;
+    const int2 sgx = A.xseg[cp.xsoff + tix], sgy = A.yseg[cp.ysoff + tiy];
+    const int mx0 = sgx.x, my0 = sgy.x;     // first member (index into xo / xb, yo / yb)
+    const int nmx = sgx.y, nmy = sgy.y;     // members of this tile: <= kPTW, kPTH
+
+    __syncthreads();   // previous tile fully consumed (tables, source tile, possibly the LUT slice)
+    if (cpi != cur_cp) {
+      cur_cp = cpi;
+      const float* __restrict__ src = A.plut + (size_t)cpi * 288 * PL;
+      for (int i = tid; i < 288 * (PL / 4); i += kPNT) {
+        const int r = i / (PL / 4), q = i - r * (PL / 4);
+        *reinterpret_cast<float4*>(s_lut + r * PITCH + 4 * q) = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * PL) + q);
+      }
+    }
+    if (tid < kPTW) {
+      const int m = mx0 + min(tid, nmx - 1);
+      s_mxo[tid] = A.xo[m];
+      s_mxb[tid] = A.xb[m];
+    } else if (tid < kPTW + kPTH) {
+      const int j = tid - kPTW;
+      const int m = my0 + min(j, nmy - 1);
+      s_myo[j] = A.yo[m];
+      s_myb[j] = A.yb[m];
+    }
+    const int xb_first = A.xb[mx0], xb_last = A.xb[mx0 + nmx - 1];
+    const int yb_first = A.yb[my0], yb_last = A.yb[my0 + nmy - 1];
+    const int sx0 = xb_first - (R - 1), sy0 = yb_first - (R - 1);
+    const int need_w = xb_last - xb_first + N, need_h = yb_last - yb_first + N;   // <= sw, sh by construction of the plan
+    const int64_t src0 = (int64_t)f * A.in_sn;
+    dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
+      constexpr int FMT = decltype(ftag)::value;
+      for (int i = tid; i < need_w * need_h; i += kPNT) {
+        const int sy = i / need_w, sx = i - sy * need_w;
+        const int gx = clampi(sx0 + sx, 0, A.w - 1), gy = clampi(sy0 + sy, 0, A.h - 1);
+        const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
+        const int d = sy * SW + sx;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float v = load_px_t<FMT>(A.in, off + c * A.in_sc, A.io.in_max);
+          s_src[c * PLANE + d] = v;
+          if constexpr (POWT) {
+            const float cc = 0.1f + v, dd = 1.1f - v;
+            const float pc = pow32(cc), pd = pow32(dd);
+            s_pow[d] = make_float4(pc, pd, pc * cc, pd * dd);
+          }
+        }
+      }
+    });
+    __syncthreads();
+
+    const int lx = tid & (kPTW - 1);
+#pragma unroll 1
+    for (int ly = tid / kPTW; ly < nmy; ly += kPNT / kPTW) {
+      if (lx >= nmx) continue;
+      const int ox = s_mxo[lx], oy = s_myo[ly];
+      const int bx = s_mxb[lx], by = s_myb[ly];
+      const int row = A.kmap[((int64_t)f * ch + (by + 1)) * cw + (bx + 1)];
+      if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
+      const int woff = (by - yb_first) * SW + (bx - xb_first);   // window tap (0, 0)
+      const float* __restrict__ kb = s_src + woff;
+      const float4* __restrict__ wr = reinterpret_cast<const float4*>(s_lut + row * PITCH);
+      float res[C];
+      float hi[C], lo[C], hi2[C], lo2[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) res[c] = hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
+#pragma unroll
+      for (int q = 0; q < TAPS / 4; ++q) {
+        const float4 w4 = wr[q];
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (AR) {
+          const float4 a4 = wr[TAPS / 4 + q];
+          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int t = q * 4 + e;
+          const int so = (t % N) * SW + (t / N);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float s = kb[c * PLANE + so];
+            res[c] = fmaf(s, wv[e], res[c]);
+            if constexpr (AR) {
+              if constexpr (POWT) {
+                const float4 pw = s_pow[woff + so];
+                hi[c] = fmaf(pw.x, av[e], hi[c]);
+                lo[c] = fmaf(pw.y, av[e], lo[c]);
+                hi2[c] = fmaf(pw.z, av[e], hi2[c]);
+                lo2[c] = fmaf(pw.w, av[e], lo2[c]);
+              } else {
+                const float cc = 0.1f + s, dd = 1.1f - s;
+                const float pc = pow32(cc), pd = pow32(dd);
+                hi[c] = fmaf(pc, av[e], hi[c]);
+                lo[c] = fmaf(pd, av[e], lo[c]);
+                hi2[c] = fmaf(pc * cc, av[e], hi2[c]);
+                lo2[c] = fmaf(pd * dd, av[e], lo2[c]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float r = res[c];
+        if constexpr (AR) {
+          const float hiv = __fdividef(hi2[c], hi[c]) - 0.1f;
+          const float lov = 1.1f - __fdividef(lo2[c], lo[c]);
+          const float cl = fminf(fmaxf(r, lov), hiv);
+          r = r * (1.0f - A.ar_strength) + cl * A.ar_strength;
+        } else {
+          r = fminf(fmaxf(r, 0.f), 1.f);
+        }
+        store_px(A.out, (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r, A.io.out_fmt, A.io.out_max);
+      }
+    }
+  }
+}
+
+// ---- the plan: phase classes of a geometry, cached on the weight handle -------------------------------------------------
+struct AxisPlan {
+  std::vector<int> off;      // [ncls + 1] member offsets
+  std::vector<int> o, b;     // members: output coordinate, base texel
+  std::vector<float> rep;    // representative sub-pixel phase of every class
+  std::vector<int> seg_off;  // [ncls + 1] segment offsets
+  std::vector<int2> seg;     // member segments (first member, count): the side of a member tile
+  int max_need = 0;          // largest staged extent a segment needs: b_last - b_first + N
+  bool ok = false;
+  bool node_spread = false;  // some class holds SEVERAL phases within fp32 noise of a LUT node (8 * sub ~ integer)
+};
+
+// Classes = runs of distinct sub-pixel phases closer than kClusterGap; never joined across the 0 / 1 wrap (at odd integer
+// ratios `pos - 0.5` is mathematically an integer for every s-th output coordinate and fp32 rounding puts some of them
+// at sub = 0.99999 of base b - 1 and the others at sub = 0.00001 of base b: different windows, hence two classes whose
+// members interleave irregularly).  Members of a class are cut into segments of at most `tile` members whose base
+// texels span at most tile * q + N source texels (q = the typical member distance), so a sparse class simply yields
+// shorter segments.
+AxisPlan build_axis(int O, int I, int tile, int N) {
+  AxisPlan ap;
+  std::vector<float> sub(O);
+  std::vector<int> base(O);
+  for (int o = 0; o < O; ++o) zoom_pos_host(o, O, I, base[o], sub[o]);
+  std::vector<float> u(sub);
+  std::sort(u.begin(), u.end());
+  u.erase(std::unique(u.begin(), u.end()), u.end());
+  std::vector<float> lo, hi;
+  for (size_t i = 0; i < u.size(); ++i) {
+    if (i == 0 || u[i] - u[i - 1] > kClusterGap) {
+      lo.push_back(u[i]);
+      hi.push_back(u[i]);
+    } else {
+      hi.back() = u[i];
+    }
+  }
+  const int ncls = (int)lo.size();
+  if (ncls > kMaxClasses) return ap;
+  for (int c = 0; c < ncls; ++c)
+    if (hi[c] - lo[c] > kMaxSpread) return ap;
+  ap.off.assign(ncls + 1, 0);
+  std::vector<int> cls(O);
+  for (int o = 0; o < O; ++o) {
+    int c = 0;
+    while (c + 1 < ncls && sub[o] > hi[c]) ++c;
+    cls[o] = c;
+    ap.off[c + 1]++;
+  }
+  for (int c = 0; c < ncls; ++c) ap.off[c + 1] += ap.off[c];
+  ap.o.resize(O);
+  ap.b.resize(O);
+  std::vector<int> fill(ap.off.begin(), ap.off.end() - 1);
+  for (int o = 0; o < O; ++o) {
+    ap.o[fill[cls[o]]] = o;
+    ap.b[fill[cls[o]]++] = base[o];
+  }
+  // typical base distance of neighbouring members (the median over all classes)
+  std::vector<int> steps;
+  for (int c = 0; c < ncls; ++c)
+    for (int m = ap.off[c] + 1; m < ap.off[c + 1]; ++m) steps.push_back(ap.b[m] - ap.b[m - 1]);
+  int q = 1;
+  if (!steps.empty()) {
+    std::nth_element(steps.begin(), steps.begin() + steps.size() / 2, steps.end());
+    q = std::max(1, steps[steps.size() / 2]);
+  }
+  if (q > kMaxStep) return ap;
+  const int limit = tile * q + N;
+  ap.seg_off.assign(1, 0);
+  for (int c = 0; c < ncls; ++c) {
+    // mid-range representative: halves the worst-case distance to a member; exact when the class is a single value
+    ap.rep.push_back(lo[c] == hi[c] ? lo[c] : 0.5f * (lo[c] + hi[c]));
+    // At a LUT node the sampler's blend weight of the neighbouring node is ~0 and PROPORTIONAL to the distance from the
+    // node: the members of such a class have weights 0 ... 2e-4 there, and one representative cannot stand for them.
+    // Harmless for the convolution (continuous in the weights) but not for the anti-ringing LUT, whose weights feed
+    // 32nd powers (see the file header): the -AR variants take the general path for such geometries.
+    const float u8 = 8.0f * ap.rep.back();
+    if (lo[c] != hi[c] && fabsf(u8 - rintf(u8)) < 4e-3f) ap.node_spread = true;
+    const int m1 = ap.off[c + 1];
+    for (int m = ap.off[c]; m < m1;) {
+      int cnt = 1;
+      while (cnt < tile && m + cnt < m1 && ap.b[m + cnt] - ap.b[m] + N <= limit) ++cnt;
+      ap.seg.push_back(make_int2(m, cnt));
+      ap.max_need = std::max(ap.max_need, ap.b[m + cnt - 1] - ap.b[m] + N);
+      m += cnt;
+    }
+    ap.seg_off.push_back((int)ap.seg.size());
+  }
+  ap.ok = true;
+  return ap;
+}
+
+struct ZoomPlan {
+  int h = 0, w = 0, oh = 0, ow = 0;
+  const mpvp_weights* lut_ar = nullptr;
+  bool usable = false;
+  int ncp = 0, total_tiles_per_frame = 0, sw = 0, sh = 0;
+  std::vector<ClassPair> cps_host;
+  int *xo = nullptr, *xb = nullptr, *yo = nullptr, *yb = nullptr;
+  int2 *xseg = nullptr, *yseg = nullptr;
+  float* plut = nullptr;
+  ~ZoomPlan() {
+    cudaFree(xo); cudaFree(xb); cudaFree(yo); cudaFree(yb); cudaFree(xseg); cudaFree(yseg); cudaFree(plut);
+  }
+};
+struct ZoomPlanCache {
+  std::mutex mu;
+  std::vector<ZoomPlan*> plans;
+};
+void free_plan_cache(void* p) {
+  ZoomPlanCache* c = static_cast<ZoomPlanCache*>(p);
+  for (ZoomPlan* z : c->plans) delete z;
+  delete c;
+}
+
+template <class T>
+cudaError_t upload(T*& dst, const std::vector<T>& v) {
+  cudaError_t e = cudaMalloc(&dst, std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+// Build (or find) the plan of a geometry.  Returns null with no error set when the geometry does not qualify for the phase
+// path; a CUDA failure also falls back to the general path (the plan is marked unusable).
+template <int R, bool AR>
+ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, int w, int oh, int ow, int C, cudaStream_t stream) {
+  mpvp_weights* L = const_cast<mpvp_weights*>(lut);
+  static std::mutex create_mu;
+  {
+    std::lock_guard<std::mutex> lk(create_mu);
+    if (!L->zoom_plans) {
+      L->zoom_plans = new ZoomPlanCache();
+      L->zoom_plans_free = free_plan_cache;
+    }
+  }
+  ZoomPlanCache* cache = static_cast<ZoomPlanCache*>(L->zoom_plans);
+  std::lock_guard<std::mutex> lk(cache->mu);
+  for (ZoomPlan* z : cache->plans)
+    if (z->h == h && z->w == w && z->oh == oh && z->ow == ow && z->lut_ar == lut_ar) return z->usable ? z : nullptr;
+  ZoomPlan* z = new ZoomPlan();
+  z->h = h; z->w = w; z->oh = oh; z->ow = ow; z->lut_ar = lut_ar;
+  cache->plans.push_back(z);
+  constexpr int N = 2 * R;
+  const AxisPlan ax = build_axis(ow, w, kPTW, N), ay = build_axis(oh, h, kPTH, N);
+  if (env_flag("MPVP_DEBUG_ZOOM", false))
+    fprintf(stderr, "[mpvp] zoom plan %dx%d -> %dx%d: x %s (%zu classes, %zu segments, need %d), y %s (%zu classes, %zu segments, need %d)\n",
+            w, h, ow, oh, ax.ok ? "ok" : "no", ax.rep.size(), ax.seg.size(), ax.max_need, ay.ok ? "ok" : "no", ay.rep.size(),
+            ay.seg.size(), ay.max_need);
+  if (!ax.ok || !ay.ok) return nullptr;
+  if (AR && (ax.node_spread || ay.node_spread)) return nullptr;
+  const int ncx = (int)ax.rep.size(), ncy = (int)ay.rep.size();
+  z->ncp = ncx * ncy;
+  z->sw = ax.max_need | 1;   // odd pitch: member windows one or more texels apart spread over the banks
+  z->sh = ay.max_need;
+  constexpr int PL = PhaseGeom<R, AR>::PL;
+  const size_t smem = sizeof(float) * (288 * PhaseGeom<R, AR>::PITCH + (((size_t)C * z->sw * z->sh + 3) & ~(size_t)3)) +
+                      ((AR && C == 1) ? sizeof(float4) * (size_t)z->sw * z->sh : 0);
+  if (smem > 200 * 1024) return nullptr;
+  int start = 0;
+  for (int cy = 0; cy < ncy; ++cy)
+    for (int cx = 0; cx < ncx; ++cx) {
+      ClassPair cp{};
+      cp.xsoff = ax.seg_off[cx]; cp.tiles_x = ax.seg_off[cx + 1] - ax.seg_off[cx];
+      cp.ysoff = ay.seg_off[cy]; cp.tiles_y = ay.seg_off[cy + 1] - ay.seg_off[cy];
+      cp.tile_start = start;   // per frame; scaled by n at launch
+      start += cp.tiles_x * cp.tiles_y;
+      z->cps_host.push_back(cp);
+    }
+  z->total_tiles_per_frame = start;
+  float *rep_x = nullptr, *rep_y = nullptr;
+  cudaError_t e = upload(z->xo, ax.o);
+  if (e == cudaSuccess) e = upload(z->xb, ax.b);
+  if (e == cudaSuccess) e = upload(z->yo, ay.o);
+  if (e == cudaSuccess) e = upload(z->yb, ay.b);
+  if (e == cudaSuccess) e = upload(z->xseg, ax.seg);
+  if (e == cudaSuccess) e = upload(z->yseg, ay.seg);
+  if (e == cudaSuccess) e = upload(rep_x, ax.rep);
+  if (e == cudaSuccess) e = upload(rep_y, ay.rep);
+  if (e == cudaSuccess) e = cudaMalloc(&z->plut, sizeof(float) * (size_t)z->ncp * 288 * PL);
+  if (e == cudaSuccess) {
+    BuildArgs b{};
+    b.lut = lut->lut; b.lut_ar = lut_ar ? lut_ar->lut : nullptr;
+    b.rep_x = rep_x; b.rep_y = rep_y; b.plut = z->plut; b.ncx = ncx; b.ncy = ncy;
+    zoom_build_plut_kernel<R, AR><<<dim3(288, z->ncp), 64, 0, stream>>>(b);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // rep_x / rep_y are freed below; once per geometry
+  }
+  cudaFree(rep_x);
+  cudaFree(rep_y);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  z->usable = true;
+  return z;
+}
+
+template <int R, int C, int KEYMODE, bool AR>
+int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) {
+  // work items are class-pair major and cover all frames of a class pair before the next one starts
+  std::vector<ClassPair> cps(z->cps_host);
+  long long total = 0;
+  for (ClassPair& cp : cps) {
+    MPVP_REQUIRE(total < (1LL << 30), "batch too large for the phase path");
+    cp.tile_start = (int)total;
+    total += (long long)cp.tiles_x * cp.tiles_y * a.n;
+  }
+  MPVP_REQUIRE(total < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", total);
+  // the class-pair table depends on n: tiny stream-ordered upload (cudaMemcpyAsync from pageable memory stages the source
+  // before it returns, so the local vector may die right after)
+  ClassPair* d_cps = nullptr;
+  MPVP_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_cps), sizeof(ClassPair) * cps.size(), stream));
+  cudaError_t e = cudaMemcpyAsync(d_cps, cps.data(), sizeof(ClassPair) * cps.size(), cudaMemcpyHostToDevice, stream);
+  unsigned short* kmap = nullptr;
+  const size_t kbytes = sizeof(unsigned short) * (size_t)a.n * (a.h + 1) * (a.w + 1);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&kmap), kbytes, stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(d_cps, stream);
+    MPVP_CUDA_OK(e);
+  }
+  a.kmap = kmap;
+  a.xo = z->xo; a.xb = z->xb; a.yo = z->yo; a.yb = z->yb; a.xseg = z->xseg; a.yseg = z->yseg; a.cps = d_cps; a.ncp = z->ncp; a.plut = z->plut;
+  a.sw = z->sw; a.sh = z->sh;
+  int rc = MPVP_OK;
+  {
+    ZoomArgs k = a;
+    k.tiles_x = (a.w + 1 + kKTW - 1) / kKTW;
+    k.tiles_y = (a.h + 1 + kKTH - 1) / kKTH;
+    k.total_tiles = (long long)k.tiles_x * k.tiles_y * a.n;
+    auto kern = zoom_key_kernel<R, C, KEYMODE>;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+    long long grid = (long long)sm_count(device) * (per_sm < 1 ? 1 : per_sm);
+    if (grid > k.total_tiles) grid = k.total_tiles;
+    grid = cap_grid(grid);
+    kern<<<(unsigned)grid, 256, 0, stream>>>(k);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  {
+    a.total_tiles = total;
+    constexpr int PITCH = PhaseGeom<R, AR>::PITCH;
+    const size_t smem = sizeof(float) * (288 * PITCH + (((size_t)C * a.sw * a.sh + 3) & ~(size_t)3)) +
+                        ((AR && C == 1) ? sizeof(float4) * (size_t)a.sw * a.sh : 0);
+    auto kern = zoom_phase_kernel<R, C, AR>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPNT, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+      set_error("ravu-zoom phase kernel does not fit on an SM (smem %zu B): %s", smem, cudaGetErrorString(e));
+      rc = MPVP_E_UNSUPPORTED;
+    } else {
+      long long grid = (long long)sm_count(device) * per_sm;
+      if (grid > total) grid = total;
+      grid = cap_grid(grid);
+      kern<<<(unsigned)grid, kPNT, smem, stream>>>(a);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  e = cudaGetLastError();
+  cudaFreeAsync(kmap, stream);
+  cudaFreeAsync(d_cps, stream);
+  if (rc != MPVP_OK) return rc;
+  MPVP_CUDA_OK(e);
+  return MPVP_OK;
+}
+
+template <int R, int C, int KEYMODE, bool AR>
+int launch_zoom(const ZoomArgs& a, const mpvp_weights* lut, const mpvp_weights* lut_ar, int device, cudaStream_t stream, bool half_lut) {
+  // MPVP_ZOOM_PHASE=0 forces the general per-pixel path (A/B switch and cross-check)
+  if (env_flag("MPVP_ZOOM_PHASE", true) && !env_flag("MPVP_ZOOM_TEX", false)) {
+    if (ZoomPlan* z = get_plan<R, AR>(lut, lut_ar, a.h, a.w, a.oh, a.ow, C, stream))
+      return launch_zoom_phase<R, C, KEYMODE, AR>(a, z, device, stream);
+  }
+  return launch_zoom_general<R, C, KEYMODE, AR>(a, device, stream, half_lut);
 }
 
 }  // namespace
@@ -339,8 +936,10 @@ extern "C" int mpvp_ravu_zoom_launch_io(const mpvp_weights* lut, const mpvp_weig
   MPVP_REQUIRE(lut->lut_w == B * 9 && lut->lut_h == 2592, "LUT is %dx%d, expected %dx2592", lut->lut_w, lut->lut_h,
                B * 9);
   MPVP_REQUIRE(!lut_ar || (lut_ar->lut_w == lut->lut_w && lut_ar->lut_h == lut->lut_h), "lut_ar geometry differs");
+  MPVP_REQUIRE(!lut_ar || radius == 2, "RAVU-Zoom-AR exists for radius 2 only (the reference ships no r3 anti-ringing LUT)");
   MPVP_REQUIRE(key->n_gauss == 16 && key->n_strength == 4 && key->n_strength_thr == 3,
                "key params do not describe a RAVU-Zoom hook");
+  if (int rck = check_fast_key(key)) return rck;
   if (n == 0) return MPVP_OK;
   DeviceGuard guard(lut->device);
   MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
@@ -362,18 +961,15 @@ extern "C" int mpvp_ravu_zoom_launch_io(const mpvp_weights* lut, const mpvp_weig
   const int dev = lut->device;
   const int ar = lut_ar ? 1 : 0;
   switch ((radius * 3 + key_mode) * 2 + ar) {
-    case 12: return launch_zoom<2, 1, 0, false>(a, dev, st, half_lut);
-    case 13: return launch_zoom<2, 1, 0, true>(a, dev, st, half_lut);
-    case 14: return launch_zoom<2, 3, 1, false>(a, dev, st, half_lut);
-    case 15: return launch_zoom<2, 3, 1, true>(a, dev, st, half_lut);
-    case 16: return launch_zoom<2, 3, 2, false>(a, dev, st, half_lut);
-    case 17: return launch_zoom<2, 3, 2, true>(a, dev, st, half_lut);
-    case 18: return launch_zoom<3, 1, 0, false>(a, dev, st, half_lut);
-    case 19: return launch_zoom<3, 1, 0, true>(a, dev, st, half_lut);
-    case 20: return launch_zoom<3, 3, 1, false>(a, dev, st, half_lut);
-    case 21: return launch_zoom<3, 3, 1, true>(a, dev, st, half_lut);
-    case 22: return launch_zoom<3, 3, 2, false>(a, dev, st, half_lut);
-    case 23: return launch_zoom<3, 3, 2, true>(a, dev, st, half_lut);
+    case 12: return launch_zoom<2, 1, 0, false>(a, lut, lut_ar, dev, st, half_lut);
+    case 13: return launch_zoom<2, 1, 0, true>(a, lut, lut_ar, dev, st, half_lut);
+    case 14: return launch_zoom<2, 3, 1, false>(a, lut, lut_ar, dev, st, half_lut);
+    case 15: return launch_zoom<2, 3, 1, true>(a, lut, lut_ar, dev, st, half_lut);
+    case 16: return launch_zoom<2, 3, 2, false>(a, lut, lut_ar, dev, st, half_lut);
+    case 17: return launch_zoom<2, 3, 2, true>(a, lut, lut_ar, dev, st, half_lut);
+    case 18: return launch_zoom<3, 1, 0, false>(a, lut, lut_ar, dev, st, half_lut);
+    case 20: return launch_zoom<3, 3, 1, false>(a, lut, lut_ar, dev, st, half_lut);
+    case 22: return launch_zoom<3, 3, 2, false>(a, lut, lut_ar, dev, st, half_lut);
   }
   return MPVP_E_INVALID;
 }

@@ -182,6 +182,7 @@ class HookFile:
         self.passes = passes
         self.textures = textures
         self._variant = None
+        self._content_key = None
 
     # -- parsing ---------------------------------------------------------------------------
     @classmethod
@@ -273,6 +274,29 @@ class HookFile:
         if self._variant is None:
             self._variant = classify(self)
         return self._variant
+
+    @property
+    def content_key(self) -> str:
+        """Identity of everything the kernels consume from this file (LUT payloads or NNEDI3 weights, key constants,
+        family parameters): two hooks with the same key are interchangeable on the device, whatever their path --
+        which is what the device weight cache is keyed on (every ``parse_text()`` hook has the path '<string>')."""
+        if self._content_key is None:
+            v = self.variant
+            h = hashlib.sha256()
+            h.update(repr((v.family, v.plane, v.radius, v.ar, v.ar_strength, v.ar_taps, v.scale, v.strength_thr,
+                           v.strength_log2_scale, v.coherence_thr, v.n_strength, v.nns, v.win)).encode())
+            if v.gauss is not None:
+                h.update(np.ascontiguousarray(v.gauss, dtype=np.float32).tobytes())
+            for tex in (v.lut, v.lut_ar):
+                if tex is not None:
+                    h.update(repr((tex.name, tex.width, tex.height)).encode())
+                    h.update(np.ascontiguousarray(tex.data, dtype=np.float32).tobytes())
+            for nn in (v.nn_y, v.nn_x):
+                if nn is not None:
+                    for a in (nn.w1, nn.w2, nn.b1, nn.b2):
+                        h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+            self._content_key = h.hexdigest()
+        return self._content_key
 
 
 # ----------------------------------------------------------------------------------------------
@@ -606,6 +630,14 @@ def _nnedi3_pass(p: Pass, nns: int, win: Tuple[int, int], direction: str, where:
             raise HookError(f"{where}: neuron {nidx}: malformed WS()")
         bb = _bits_to_float([int(m.group(1)), int(m.group(2))])
         b1[nidx], b2[nidx] = bb[0], bb[1]
+    # The tensor-core path feeds (x - mean) * inv_std into the contraction while the shader computes dot(x, W) * inv_std
+    # (nnedi3-nns16-win8x4.hook:30-50): the two agree only for mean-removed weights (sum_k W[n][k] = 0; the shipped
+    # files hold |sum| <= 1.4e-6).  A file that breaks this would run silently wrong: refuse it.
+    for nm, wmat in (("W1", w1), ("W2", w2)):
+        worst = float(np.abs(wmat.astype(np.float64).sum(axis=1)).max())
+        if worst > 1e-5:
+            raise HookError(f"{where}: NNEDI3 {nm} weights are not mean-removed (|sum| = {worst:.3e} > 1e-5); "
+                            "this is not a shipped mpv-prescalers weight set")
     return Nnedi3Weights(w1.reshape(nns, 8, S), w2.reshape(nns, 8, S), b1, b2)
 
 

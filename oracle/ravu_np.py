@@ -248,8 +248,13 @@ def _ravu_conv(v, lut: np.ndarray, key_s: List[np.ndarray], col_s: List[np.ndarr
     return res, key
 
 
-def ravu(img: np.ndarray, v, lut_precision: str = "fp16", return_intermediates: bool = False):
-    """2x upscale, [H, W(, 3)] -> [2H, 2W(, 3)], offset (-0.5, -0.5)  (``ravu-r2.hook:15-338``)."""
+def ravu(img: np.ndarray, v, lut_precision: str = "fp16", return_intermediates: bool = False, int11_override=None):
+    """2x upscale, [H, W(, 3)] -> [2H, 2W(, 3)], offset (-0.5, -0.5)  (``ravu-r2.hook:15-338``).
+
+    ``int11_override`` ([H, W(, 3)]): run steps 2-4 on THIS saved ``ravu_int11`` texture instead of the one step 1
+    produced.  The parity tests pass the device's own int11 here: steps 2/3 are then evaluated on bit-identical
+    inputs, so their buckets can be compared without the cascade that last-bit differences of the int11 VALUES
+    (different summation order in the convolution) send through the ill-conditioned parts of the key."""
     img3 = _as_planes(img)
     r = v.radius
     n, o, _ = _window_geometry("ravu", r)
@@ -262,6 +267,9 @@ def ravu(img: np.ndarray, v, lut_precision: str = "fp16", return_intermediates: 
     col = [hooked.at(t // n - o, t % n - o) for t in range(N)]
     ks = [hooked_key.at(t // n - o, t % n - o) for t in range(N)]
     int11, key1 = _ravu_conv(v, lut, ks, col)
+    if int11_override is not None:
+        int11 = _as_planes(np.asarray(int11_override, dtype=F32))
+        assert int11.shape == img3.shape
     i11 = _Plane(int11, 2 * r)
     i11_key = _Plane(_key_plane(v, int11), 2 * r)
     keys = [key1]

@@ -45,11 +45,12 @@ def on_edge_mask(key, v):
 def check_buckets(got_rows, key, v, what=""):
     """got_rows, key.row: same shape.  Returns the agreement mask.
 
-    A mismatch counts as "at a quantisation boundary" when the oracle's own continuous key coordinate is
-    within reach of fp32 rounding noise of a bucket edge.  The reach is not uniform: the angle is
-    atan2(L1 - a, b) with L1 - a computed by cancellation, so its conditioning degrades like 1/coherence
-    (an isotropic neighbourhood, mu -> 0, has no defined direction at all) and like 1/lambda (flat
-    neighbourhood); near theta = 0 = pi the sign of a vanishing b decides between sector 0 and sector 23.
+    Every comparison made with this function runs the device and the oracle on IDENTICAL inputs (the RAVU steps 2 / 3,
+    whose int11 inputs differ in the last bits between device and oracle, are checked against the oracle evaluated on
+    the device's own int11), and up to the eigenvalues the device arithmetic is the shader's, operation for operation.
+    What differs is only the last step -- sector tests on (b, L1 - a) instead of atan, eigenvalue thresholds instead of
+    sqrt / division -- so a mismatch is "at a quantisation boundary" only if the oracle's own continuous coordinate
+    lies within a few float32 ulps of a bucket edge; there is no allowance for badly conditioned keys.
     """
     same = np.asarray(got_rows) == key.row
     frac = float(same.mean())
@@ -60,12 +61,10 @@ def check_buckets(got_rows, key, v, what=""):
         on_edge = (d_angle < 1e-4) | (d_str < 1e-5) | (d_coh < 1e-5)
         counted = int((~on_edge).sum())
         assert frac >= BUCKET_MIN_AGREE or counted <= 1, f"{what}: bucket agreement {frac:.6f} < {BUCKET_MIN_AGREE}"
-        lam = np.asarray(key.lam)[~same]
-        mu = np.nan_to_num(np.asarray(key.mu)[~same])
-        near = (d_angle < 2e-2) | (d_str < 2e-3) | (d_coh < 2e-3) | (lam < 1e-3) | (mu < 2e-2)
+        near = (d_angle < 2e-3) | (d_str < 2e-4) | (d_coh < 2e-4)
         assert np.all(near), (
             f"{what}: bucket mismatch away from a quantisation boundary "
-            f"(angle {d_angle[~near]}, strength {d_str[~near]}, coherence {d_coh[~near]}, mu {mu[~near]})")
+            f"(angle {d_angle[~near]}, strength {d_str[~near]}, coherence {d_coh[~near]})")
     return same
 
 

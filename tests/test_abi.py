@@ -91,3 +91,33 @@ def test_plane_io_descriptor_rules():
         PlaneIO(torch.uint8, bit_depth=10)
     with pytest.raises(TypeError):
         PlaneIO(torch.int32)
+
+
+@pytest.mark.parametrize("name", ["ravu-lite-ar-r3.hook", "ravu-r3.hook", "ravu-r4.hook", "compute/ravu-3x-r2.hook", "ravu-zoom-r2.hook"])
+def test_key_params_finalize_reproduces_the_python_tables(name):
+    """mpvp_key_params_finalize (pure host arithmetic) derives the same l1_thr[] / coh_ratio[] from the shader constants
+    as the NumPy bisection the Python host uses, so a C caller needs nothing from the Python package."""
+    from mpv_prescalers_b200 import HookFile, _native
+    from mpv_prescalers_b200.api import _key_params
+    from tests.conftest import hook_path
+
+    v = HookFile.parse(hook_path(name)).variant
+    want = _key_params(v)
+    kp = _key_params(v)
+    kp.n_l1_thr = 0
+    for i in range(8):
+        kp.l1_thr[i] = 0.0
+    kp.coh_ratio[0] = kp.coh_ratio[1] = 0.0
+    rc = _native.lib().mpvp_key_params_finalize(ctypes.byref(kp))
+    assert rc == 0, _native.lib().mpvp_last_error()
+    assert kp.n_l1_thr == want.n_l1_thr == v.n_strength - 1
+    assert list(kp.l1_thr) == list(want.l1_thr)
+    assert list(kp.coh_ratio) == list(want.coh_ratio)
+
+
+def test_key_params_finalize_rejects_nonsense():
+    from mpv_prescalers_b200 import _native
+
+    kp = _native.KeyParams()
+    assert _native.lib().mpvp_key_params_finalize(ctypes.byref(kp)) < 0
+    assert b"n_strength" in _native.lib().mpvp_last_error()

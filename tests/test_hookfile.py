@@ -181,3 +181,36 @@ def test_flavours_carry_identical_payloads_and_constants():
                 assert np.array_equal(v.nn_y.w1, base.nn_y.w1) and np.array_equal(v.nn_x.w2, base.nn_x.w2)
             checked += 1
     assert checked >= 40
+
+
+def test_content_key_identifies_the_weights_not_the_path(hooks):
+    """The device weight cache is keyed on content: in-memory hooks (all of path '<string>') must not share entries
+    unless they really hold the same weights and constants."""
+    from mpv_prescalers_b200.hookfile import HookFile
+
+    ta = open(hooks("ravu-lite-r3.hook")).read()
+    tb = open(hooks("ravu-lite-ar-r3.hook")).read()
+    a, a2, b = HookFile.parse_text(ta), HookFile.parse_text(ta), HookFile.parse_text(tb)
+    assert a.path == b.path == "<string>"
+    assert a.content_key == a2.content_key
+    assert a.content_key != b.content_key            # same LUT payload, different kernel parameters (anti-ringing)
+    assert HookFile.parse(hooks("ravu-lite-r3.hook")).content_key == a.content_key
+    c = HookFile.parse_text(open(hooks("ravu-lite-r2.hook")).read())
+    assert c.content_key != a.content_key
+
+
+def test_nnedi3_weights_must_be_mean_removed(hooks):
+    """The tensor-core path feeds (x - mean) / sigma into the contraction, which equals the shader's dot(x, W) / sigma
+    only for weight rows that sum to zero: a file that breaks this is refused, not silently mis-run."""
+    import re
+    import struct
+
+    from mpv_prescalers_b200.hookfile import HookError, HookFile
+
+    text = open(hooks("nnedi3-nns16-win8x4.hook")).read()
+    HookFile.parse_text(text).variant  # the shipped file passes
+    one = struct.unpack("<i", struct.pack("<f", 1.0))[0]
+    bad, n = re.subn(r"sum1=W\(0,(-?\d+),", f"sum1=W(0,{one},", text, count=1)
+    assert n == 1
+    with pytest.raises(HookError, match="mean-removed"):
+        HookFile.parse_text(bad).variant
