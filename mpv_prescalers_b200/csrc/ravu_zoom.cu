@@ -381,7 +381,7 @@ int launch_zoom_general(const ZoomArgs& a, int device, cudaStream_t stream, bool
 // =====================================================================================================================
 // PHASE path
 // =====================================================================================================================
-constexpr int kPTW = 64, kPTH = 16, kPNT = 256;   // member tile (64 x 16 output pixels of one class pair), threads
+constexpr int kPTW = 64, kPTH = 16;   // member tile: 64 x 16 output pixels of one class pair
 constexpr int kMaxClasses = 8;                    // per axis
 constexpr int kMaxStep = 3;                       // base-texel distance of neighbouring class members
 constexpr float kClusterGap = 2.5e-4f;            // sub-pixel phases closer than this belong to one class ...
@@ -474,20 +474,53 @@ __global__ void zoom_build_plut_kernel(const BuildArgs A) {
 }
 
 // ---- convolution of one class pair's members ------------------------------------------------------------------------
-// PITCH: floats per phase-LUT row in shared memory, a multiple of 4 (16-byte weight loads) chosen so that PITCH / 4 is odd:
-// the 32 lanes of a warp gather 32 different rows, an odd 16-byte pitch spreads them over all bank groups.
-template <int R, bool AR>
+// The gather of 32 different phase-LUT rows per warp is what bounds this kernel (shared-memory wavefronts), so the rows are
+// kept compact.  MIX = mixed-precision rows: the four central taps (|w| up to 1.45) stay float32, the others (|w| <= 0.36,
+// mostly << 0.1) are stored as binary16 -- an absolute rounding error <= 1.2e-4 on the largest of them, ~1e-4 on the
+// output in the worst case (the anti-ringing LUT, whose weights feed 32nd powers, always stays float32).  Row layout:
+//   MIX : [c0 c1 c2 c3 : float32][the other TAPS - 4 taps in tap order : binary16][pad]      r3: 80 B, r2: 48 B
+//   !MIX: [TAPS float32]([TAPS float32 anti-ringing weights])
+// The pitch in 16-byte units is odd, so the rows spread over all bank groups.
+template <int R>
+__host__ __device__ constexpr bool central_tap(int t) {
+  const int N = 2 * R, i = t / N, j = t % N;
+  return (i == R - 1 || i == R) && (j == R - 1 || j == R);
+}
+template <int R, bool AR, bool MIX>
 struct PhaseGeom {
   static constexpr int TAPS = 4 * R * R;
-  static constexpr int PL = TAPS * (AR ? 2 : 1);
-  static constexpr int PITCH = ((PL / 4) | 1) * 4;
+  static constexpr int PL = TAPS * (AR ? 2 : 1);                       // floats per row of the global phase LUT
+  static constexpr int QUADS = MIX ? (16 + 2 * (TAPS - 4) + 15) / 16 : PL / 4;   // 16-byte units actually read per row
+  static constexpr int PITCH = (QUADS | 1) * 4;                        // floats per row in shared memory
 };
 
-template <int R, int C, bool AR>
-__global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant__ ZoomArgs A) {
+__device__ __forceinline__ void store_px_wb(void* __restrict__ p, int64_t off, float v, int fmt, float out_max) {
+  // write-back (not streaming) stores: a class pair writes every P-th pixel of a row, the other classes fill in the
+  // rest of each 32-byte sector a little later -- the sectors should wait in L2 for that instead of being evicted first
+  switch (fmt) {
+    case MPVP_FMT_F32: static_cast<float*>(p)[off] = v; break;
+    case MPVP_FMT_F16: reinterpret_cast<unsigned short*>(p)[off] = __half_as_ushort(__float2half_rn(v)); break;
+    case MPVP_FMT_U8: static_cast<unsigned char*>(p)[off] = (unsigned char)quant_px(v, out_max); break;
+    default: static_cast<unsigned short*>(p)[off] = (unsigned short)quant_px(v, out_max); break;
+  }
+}
+
+// SWT: compile-time pitch of the staged source tile (0 = runtime A.sw): immediate offsets for the window loads.
+// STRIP: member rows per thread (the CTA has kPTW * kPTH / STRIP threads).
+#ifndef MPVP_X_ZOOM_STRIP
+#define MPVP_X_ZOOM_STRIP 4
+#endif
+constexpr int kStrip = MPVP_X_ZOOM_STRIP;
+constexpr int kPNT2 = kPTW * kPTH / kStrip;
+template <int R, int C, bool AR, int SWT, bool MIX>
+__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A) {
+  constexpr int kPNT = kPNT2;
   constexpr int N = 2 * R, TAPS = N * N;
-  constexpr int PL = PhaseGeom<R, AR>::PL, PITCH = PhaseGeom<R, AR>::PITCH;
+  using PG = PhaseGeom<R, AR, MIX>;
+  constexpr int PL = PG::PL, PITCH = PG::PITCH;
   constexpr bool POWT = AR && C == 1;   // anti-ringing powers once per staged source pixel (luma); 3-channel: on the fly
+  constexpr int STRIP = kStrip;
+  static_assert(!MIX || !AR, "the anti-ringing weights stay float32");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_lut = reinterpret_cast<float*>(smem_raw);            // [288][PITCH]
@@ -496,7 +529,8 @@ __global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant_
   __shared__ int s_mxo[kPTW], s_mxb[kPTW], s_myo[kPTH], s_myb[kPTH];
 
   const int tid = threadIdx.x;
-  const int SW = A.sw, PLANE = A.sw * A.sh;
+  const int SW = SWT ? SWT : A.sw;
+  const int PLANE = SW * A.sh;
   const int cw = A.w + 1, ch = A.h + 1;
   // contiguous run of work items (class-pair major): at most a couple of phase-LUT reloads per CTA
   const long long T = A.total_tiles;
@@ -519,9 +553,24 @@ __global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant_
     if (cpi != cur_cp) {
       cur_cp = cpi;
       const float* __restrict__ src = A.plut + (size_t)cpi * 288 * PL;
-      for (int i = tid; i < 288 * (PL / 4); i += kPNT) {
-        const int r = i / (PL / 4), q = i - r * (PL / 4);
-        *reinterpret_cast<float4*>(s_lut + r * PITCH + 4 * q) = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * PL) + q);
+      if constexpr (MIX) {
+        for (int r = tid; r < 288; r += kPNT) {
+          const float* __restrict__ g = src + (size_t)r * PL;
+          float* d = s_lut + r * PITCH;
+          __half* dh = reinterpret_cast<__half*>(d + 4);
+          int nc = 0, nh = 0;
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            const float wv = __ldg(g + t);
+            if (central_tap<R>(t)) d[nc++] = wv;
+            else dh[nh++] = __float2half_rn(wv);
+          }
+        }
+      } else {
+        for (int i = tid; i < 288 * (PL / 4); i += kPNT) {
+          const int r = i / (PL / 4), q = i - r * (PL / 4);
+          *reinterpret_cast<float4*>(s_lut + r * PITCH + 4 * q) = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * PL) + q);
+        }
       }
     }
     if (tid < kPTW) {
@@ -561,51 +610,78 @@ __global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant_
     __syncthreads();
 
     const int lx = tid & (kPTW - 1);
-#pragma unroll 1
-    for (int ly = tid / kPTW; ly < nmy; ly += kPNT / kPTW) {
-      if (lx >= nmx) continue;
-      const int ox = s_mxo[lx], oy = s_myo[ly];
-      const int bx = s_mxb[lx], by = s_myb[ly];
-      const int row = A.kmap[((int64_t)f * ch + (by + 1)) * cw + (bx + 1)];
+    const int ly0 = (tid / kPTW) * STRIP;            // this thread's member rows: ly0 .. ly0 + STRIP - 1
+    if (lx >= nmx || ly0 >= nmy) continue;
+    const int cnt = min(STRIP, nmy - ly0);
+    const int ox = s_mxo[lx], bx = s_mxb[lx];
+    const int by0 = s_myb[ly0];
+
+    // the LUT rows of the strip's pixels come from the key map in global memory (L2): all loads issued up front
+    int rows[STRIP];
+#pragma unroll
+    for (int k = 0; k < STRIP; ++k)
+      rows[k] = A.kmap[((int64_t)f * ch + (s_myb[ly0 + (k < cnt ? k : 0)] + 1)) * cw + (bx + 1)];
+
+    // weights of LUT row `row` applied to the window whose tap (i, j) is Wn(c, i, j); finishes and stores one output pixel
+    auto pixel = [&](int k, int row, auto Wn) {
+      const int oy = s_myo[ly0 + k];
+      [[maybe_unused]] const int by = s_myb[ly0 + k];
       if (A.bucket) A.bucket[((int64_t)f * A.oh + oy) * A.ow + ox] = row;
-      const int woff = (by - yb_first) * SW + (bx - xb_first);   // window tap (0, 0)
-      const float* __restrict__ kb = s_src + woff;
       const float4* __restrict__ wr = reinterpret_cast<const float4*>(s_lut + row * PITCH);
       float res[C];
       float hi[C], lo[C], hi2[C], lo2[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) res[c] = hi[c] = lo[c] = hi2[c] = lo2[c] = 0.f;
+      if constexpr (MIX) {
+        const float4 wc = wr[0];
+        const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+        int nc = 0, nh = 0;
+        uint4 hq = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int q = 0; q < TAPS / 4; ++q) {
-        const float4 w4 = wr[q];
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        float av[4] = {0.f, 0.f, 0.f, 0.f};
-        if constexpr (AR) {
-          const float4 a4 = wr[TAPS / 4 + q];
-          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+        for (int t = 0; t < TAPS; ++t) {
+          float wt;
+          if (central_tap<R>(t)) {
+            wt = wcv[nc++];
+          } else {
+            if ((nh & 7) == 0) hq = *reinterpret_cast<const uint4*>(&wr[1 + nh / 8]);
+            const unsigned int pr = (nh & 7) < 2 ? hq.x : ((nh & 7) < 4 ? hq.y : ((nh & 7) < 6 ? hq.z : hq.w));
+            const __half2 h2 = *reinterpret_cast<const __half2*>(&pr);
+            wt = (nh & 1) ? __high2float(h2) : __low2float(h2);
+            ++nh;
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) res[c] = fmaf(Wn(c, t / N, t % N), wt, res[c]);
         }
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int t = q * 4 + e;
-          const int so = (t % N) * SW + (t / N);
+        for (int q = 0; q < TAPS / 4; ++q) {
+          const float4 w4 = wr[q];
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          [[maybe_unused]] float av[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (AR) {
+            const float4 a4 = wr[TAPS / 4 + q];
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          }
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float s = kb[c * PLANE + so];
-            res[c] = fmaf(s, wv[e], res[c]);
-            if constexpr (AR) {
-              if constexpr (POWT) {
-                const float4 pw = s_pow[woff + so];
+          for (int e = 0; e < 4; ++e) {
+            const int t = q * 4 + e;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const float sv = Wn(c, t / N, t % N);
+              res[c] = fmaf(sv, wv[e], res[c]);
+              if constexpr (AR) {
+                float4 pw;
+                if constexpr (POWT) {
+                  pw = s_pow[(by - yb_first + t % N) * SW + (bx - xb_first) + t / N];
+                } else {
+                  const float cc = 0.1f + sv, dd = 1.1f - sv;
+                  const float pc = pow32(cc), pd = pow32(dd);
+                  pw = make_float4(pc, pd, pc * cc, pd * dd);
+                }
                 hi[c] = fmaf(pw.x, av[e], hi[c]);
                 lo[c] = fmaf(pw.y, av[e], lo[c]);
                 hi2[c] = fmaf(pw.z, av[e], hi2[c]);
                 lo2[c] = fmaf(pw.w, av[e], lo2[c]);
-              } else {
-                const float cc = 0.1f + s, dd = 1.1f - s;
-                const float pc = pow32(cc), pd = pow32(dd);
-                hi[c] = fmaf(pc, av[e], hi[c]);
-                lo[c] = fmaf(pd, av[e], lo[c]);
-                hi2[c] = fmaf(pc * cc, av[e], hi2[c]);
-                lo2[c] = fmaf(pd * dd, av[e], lo2[c]);
               }
             }
           }
@@ -622,7 +698,32 @@ __global__ void __launch_bounds__(kPNT) zoom_phase_kernel(const __grid_constant_
         } else {
           r = fminf(fmaxf(r, 0.f), 1.f);
         }
-        store_px(A.out, (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r, A.io.out_fmt, A.io.out_max);
+        store_px_wb(A.out, (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)oy * A.out_sy + ox, r, A.io.out_fmt, A.io.out_max);
+      }
+    };
+
+    // The member rows of a strip usually sit on consecutive base texels (integer ratios): their windows overlap in all but
+    // one row, so ONE (N + cnt - 1) x N register window serves the whole strip (warp-uniform test: a warp shares ly0).
+    bool consec = (C == 1);
+    for (int k = 1; k < cnt; ++k) consec = consec && (s_myb[ly0 + k] == by0 + k);
+    if (consec) {
+      if constexpr (C == 1) {
+        const float* __restrict__ kb = s_src + (by0 - yb_first) * SW + (bx - xb_first);
+        float win[N + STRIP - 1][N];
+#pragma unroll
+        for (int j = 0; j < N + STRIP - 1; ++j)
+#pragma unroll
+          for (int i = 0; i < N; ++i) win[j][i] = (j < N + cnt - 1) ? kb[j * SW + i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < STRIP; ++k)
+          if (k < cnt) pixel(k, rows[k], [&](int, int i, int j) { return win[k + j][i]; });
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < STRIP; ++k) {
+        if (k >= cnt) break;
+        const float* __restrict__ kb = s_src + (s_myb[ly0 + k] - yb_first) * SW + (bx - xb_first);
+        pixel(k, rows[k], [&](int c, int i, int j) { return kb[c * PLANE + j * SW + i]; });
       }
     }
   }
@@ -780,8 +881,8 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
   z->ncp = ncx * ncy;
   z->sw = ax.max_need | 1;   // odd pitch: member windows one or more texels apart spread over the banks
   z->sh = ay.max_need;
-  constexpr int PL = PhaseGeom<R, AR>::PL;
-  const size_t smem = sizeof(float) * (288 * PhaseGeom<R, AR>::PITCH + (((size_t)C * z->sw * z->sh + 3) & ~(size_t)3)) +
+  constexpr int PL = PhaseGeom<R, AR, false>::PL;
+  const size_t smem = sizeof(float) * (288 * PhaseGeom<R, AR, false>::PITCH + (((size_t)C * z->sw * z->sh + 3) & ~(size_t)3)) +
                       ((AR && C == 1) ? sizeof(float4) * (size_t)z->sw * z->sh : 0);
   if (smem > 200 * 1024) return nullptr;
   int start = 0;
@@ -867,22 +968,36 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
   }
   {
     a.total_tiles = total;
-    constexpr int PITCH = PhaseGeom<R, AR>::PITCH;
-    const size_t smem = sizeof(float) * (288 * PITCH + (((size_t)C * a.sw * a.sh + 3) & ~(size_t)3)) +
-                        ((AR && C == 1) ? sizeof(float4) * (size_t)a.sw * a.sh : 0);
-    auto kern = zoom_phase_kernel<R, C, AR>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPNT, smem);
-    if (e != cudaSuccess || per_sm < 1) {
-      set_error("ravu-zoom phase kernel does not fit on an SM (smem %zu B): %s", smem, cudaGetErrorString(e));
-      rc = MPVP_E_UNSUPPORTED;
-    } else {
+    // MPVP_ZOOM_MIX=0: all phase-LUT weights stay float32 in shared memory (A/B switch for the binary16 outer taps)
+    const bool mix = !AR && env_flag("MPVP_ZOOM_MIX", true);
+    constexpr int kSWT = kPTW + 2 * R + 3;   // compile-time tile pitch (odd) when neighbouring members sit one texel apart
+    const bool fixed_pitch = a.sw <= kSWT;
+    if (fixed_pitch) a.sw = kSWT;
+    auto launch = [&](auto kern, int pitch) {
+      const size_t smem = sizeof(float) * (288 * (size_t)pitch + (((size_t)C * a.sw * a.sh + 3) & ~(size_t)3)) +
+                          ((AR && C == 1) ? sizeof(float4) * (size_t)a.sw * a.sh : 0);
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int per_sm = 0;
+      if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPNT2, smem);
+      if (e2 != cudaSuccess || per_sm < 1) {
+        set_error("ravu-zoom phase kernel does not fit on an SM (smem %zu B): %s", smem, cudaGetErrorString(e2));
+        rc = MPVP_E_UNSUPPORTED;
+        return;
+      }
       long long grid = (long long)sm_count(device) * per_sm;
       if (grid > total) grid = total;
       grid = cap_grid(grid);
-      kern<<<(unsigned)grid, kPNT, smem, stream>>>(a);
+      kern<<<(unsigned)grid, kPNT2, smem, stream>>>(a);
       g_launches.fetch_add(1, std::memory_order_relaxed);
+    };
+    if constexpr (AR) {
+      if (fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, false>, PhaseGeom<R, AR, false>::PITCH);
+      else launch(zoom_phase_kernel<R, C, AR, 0, false>, PhaseGeom<R, AR, false>::PITCH);
+    } else {
+      if (mix && fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, true>, PhaseGeom<R, AR, true>::PITCH);
+      else if (mix) launch(zoom_phase_kernel<R, C, AR, 0, true>, PhaseGeom<R, AR, true>::PITCH);
+      else if (fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, false>, PhaseGeom<R, AR, false>::PITCH);
+      else launch(zoom_phase_kernel<R, C, AR, 0, false>, PhaseGeom<R, AR, false>::PITCH);
     }
   }
   e = cudaGetLastError();
