@@ -190,6 +190,23 @@ int mpvp_nnedi3_launch_io(const mpvp_weights* nn, int direction, const void* in,
                           int w, int64_t in_stride_n, int64_t in_stride_y, int64_t out_stride_n,
                           int64_t out_stride_y, const mpvp_io* io, void* stream);
 
+/* ---- the step after the path: offset-correcting main scaler ---------------------------------
+ * ravu and nnedi3 declare //!OFFSET -0.5 -0.5 (ravu-r2.hook:325, nnedi3-nns16-win8x4.hook:95,185): texel X of their output
+ * holds the content that belongs half a texel further right / down.  mpv corrects that in its main scaler (--scale),
+ * which samples the hooked plane at the shifted position while resizing to the output size.  This entry point is that
+ * scaler: separable polyphase resampling of `planes` planes [h][w] -> [out_h][out_w] with
+ *     s(o) = (o + 0.5) * in / out - 0.5 + offset      (offset = the accumulated //!OFFSET, in texels of the input plane)
+ * clamp-to-edge, weights normalised per output coordinate, kernel not widened when downscaling (mpv's default
+ * --correct-downscaling=no; downscaling by more than 2x is refused).  Kernels as in mpv's filter_kernels.c. */
+#define MPVP_SCALER_BILINEAR 0
+#define MPVP_SCALER_CATMULL_ROM 1 /* bicubic B=0, C=0.5 */
+#define MPVP_SCALER_MITCHELL 2    /* bicubic B=C=1/3 */
+#define MPVP_SCALER_SPLINE36 3
+#define MPVP_SCALER_LANCZOS 4     /* sinc windowed by sinc, radius 3 */
+int mpvp_resample_launch_io(int device, int kernel, const void* in, void* out, int planes, int h, int w, int out_h,
+                            int out_w, float offset_x, float offset_y, int64_t in_stride_p, int64_t in_stride_y,
+                            int64_t out_stride_p, int64_t out_stride_y, const mpvp_io* io, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end path: H2D + kernel + D2H inside the call) --------- */
 int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
                         float ar_strength, const float* host_in, float* host_out, int n, int h,

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # MPVP_LIB: load an experiment build (tools/build_variant.py) instead of the product library
 LIB_PATH = os.environ.get("MPVP_LIB") or os.path.join(HERE, "libmpvp.so")
-SOURCES = ["abi.cu", "ravu_lite.cu", "ravu_lite_ar.cu", "ravu_3x.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu"]
+SOURCES = ["abi.cu", "ravu_lite.cu", "ravu_lite_ar.cu", "ravu_3x.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu", "resample.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -117,6 +117,7 @@ class IoDesc(ctypes.Structure):
 
 
 FMT_F32, FMT_F16, FMT_U8, FMT_U16 = 0, 1, 2, 3
+SCALERS = {"bilinear": 0, "catmull_rom": 1, "mitchell": 2, "spline36": 3, "lanczos": 4}
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -145,6 +146,7 @@ SIGNATURES = {
     "mpvp_ravu3x_launch_io": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
     "mpvp_ravu_zoom_launch_io": (_i, [_vp, _vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _iop, _vp]),
     "mpvp_nnedi3_launch_io": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _iop, _vp]),
+    "mpvp_resample_launch_io": (_i, [_i, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i64, _i64, _i64, _i64, _iop, _vp]),
     "mpvp_ravu_lite_host": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i]),
 }
 

@@ -22,7 +22,7 @@ import torch
 from . import _native
 from .hookfile import HookError, HookFile, Variant, find_hook
 
-__all__ = ["prescale", "plan", "Plan", "upload_weights", "clear_weight_cache"]
+__all__ = ["prescale", "resample", "plan", "Plan", "upload_weights", "clear_weight_cache"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -395,6 +395,7 @@ def prescale(
     bit_depth: Optional[int] = None,
     out_bit_depth: Optional[int] = None,
     split: str = "frames",
+    correct_offset: Union[bool, str] = False,
 ):
     """Apply one mpv-prescalers hook file to a batch of frames.
 
@@ -419,24 +420,45 @@ def prescale(
                   host's texture normalisation times ``HOOKED_mul``) and float16 (mpv's rgba16f FBO precision).
                   Integer results are ``rint(clamp(v, 0, 1) * (2**out_bit_depth - 1))``.
 
+    correct_offset  ravu and nnedi3 leave their result half a texel off (``//!OFFSET -0.5 -0.5``, ravu-r2.hook:325) and
+                  rely on the host's main scaler to compensate.  ``True`` (= 'lanczos') or the name of an mpv scaler
+                  kernel ('bilinear', 'catmull_rom', 'mitchell', 'spline36', 'lanczos') runs that step (``resample()``,
+                  same size, shifted by the accumulated offset) so that the result is aligned like ravu-lite's and
+                  ``.offset`` is (0, 0); hooks without an offset are returned as they are.
+
     Returns the output tensor (same rank as the input) carrying ``.offset`` (accumulated ``//!OFFSET``,
     (x, y) in output pixels), ``.applied`` and ``.plan``; with ``return_buckets=True`` a pair
     ``(out, buckets)`` where ``buckets`` holds the LUT row of every key evaluation (RAVU families).
     """
     hk = hook if isinstance(hook, HookFile) else HookFile.parse(find_hook(hook))
     v = hk.variant
+    scaler = None
+    if correct_offset:
+        scaler = "lanczos" if correct_offset is True else str(correct_offset)
+        if scaler not in _native.SCALERS:
+            raise ValueError(f"correct_offset must be True or one of {sorted(_native.SCALERS)}")
     if devices is not None:
         from .sharding import prescale_rowsplit, prescale_sharded
 
         if return_buckets or out is not None:
             raise ValueError("return_buckets / out cannot be combined with devices=[...] (sharded results stay on their GPUs)")
         if split == "rows":
-            return prescale_rowsplit(frames, hk, output_size, list(devices), lut_precision, is_yuv,
-                                     out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
+            # the bands are gathered first: the correction filter must see real neighbouring rows across the seams
+            mid_dtype = torch.float32 if scaler else out_dtype
+            res = prescale_rowsplit(frames, hk, output_size, list(devices), lut_precision, is_yuv,
+                                    out_dtype=mid_dtype, bit_depth=bit_depth, out_bit_depth=None if scaler else out_bit_depth)
+            if scaler and getattr(res, "applied", False) and tuple(res.offset) != (0.0, 0.0):
+                pl0 = res.plan
+                want = out_dtype if out_dtype is not None else frames.dtype
+                res = resample(res, None, res.offset, scaler, out_dtype=want,
+                               out_bit_depth=out_bit_depth if out_bit_depth is not None else bit_depth)
+                res.offset, res.applied, res.plan = (0.0, 0.0), True, pl0
+            return res
         if split != "frames":
             raise ValueError("split must be 'frames' or 'rows'")
         return prescale_sharded(frames, hk, output_size, list(devices), lut_precision, is_yuv,
-                                out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth)
+                                out_dtype=out_dtype, bit_depth=bit_depth, out_bit_depth=out_bit_depth,
+                                correct_offset=correct_offset)
     x, in_shape = _normalise_input(frames, v)
     n, c, h, w = x.shape
     io = PlaneIO(x.dtype, out_dtype, bit_depth, out_bit_depth)
@@ -459,6 +481,25 @@ def prescale(
     if not torch.cuda.is_available():
         raise _native.NativeError("prescale() needs a CUDA device: there is no CPU fallback")
     host_input = x.device.type != "cuda"
+    if scaler and tuple(pl.offset) != (0.0, 0.0):
+        # hook -> float32 plane -> offset-correcting scaler -> the requested plane format (one quantisation, at the end)
+        dev = torch.device("cuda", torch.cuda.current_device()) if host_input else x.device
+        xd = x.to(dev, non_blocking=True) if host_input else (x if (x.stride(3) == 1 and x.stride(2) >= w) else x.contiguous())
+        W = upload_weights(hk, dev.index, lut_precision)
+        mid = PlaneIO(x.dtype, torch.float32, bit_depth, None)
+        with torch.cuda.device(dev):
+            res, bk = _launch(hk, pl, xd, W, return_buckets, mid)
+            res = resample(res, None, pl.offset, scaler, out_dtype=io.out_dtype, out_bit_depth=io.out_bits or None)
+        if host_input:
+            if out is not None:
+                out.copy_(res)
+                res = out
+            else:
+                res = res.cpu()
+            bk = bk.cpu() if bk is not None else None
+        res = _restore_shape(res, in_shape, c)
+        res.offset, res.applied, res.plan = (0.0, 0.0), True, pl
+        return (res, bk) if return_buckets else res
     if host_input:
         dev = torch.device("cuda", torch.cuda.current_device())
         W = upload_weights(hk, dev.index, lut_precision)
@@ -472,6 +513,53 @@ def prescale(
     res = _restore_shape(res, in_shape, c)
     res.offset, res.applied, res.plan = pl.offset, True, pl
     return (res, bk) if return_buckets else res
+
+
+def resample(frames: torch.Tensor, output_size: Optional[Tuple[int, int]] = None, offset: Tuple[float, float] = (0.0, 0.0),
+             kernel: str = "lanczos", out_dtype: Optional[torch.dtype] = None, bit_depth: Optional[int] = None,
+             out_bit_depth: Optional[int] = None) -> torch.Tensor:
+    """The step after the hook: mpv's main scaler, which also absorbs the accumulated
+    ``//!OFFSET`` of the hooked plane (ravu-r2.hook:325, nnedi3-nns16-win8x4.hook:95,185).
+
+    frames       ``[H,W]``, ``[N,H,W]`` or ``[N,C,H,W]`` planes (float32 / float16 / uint8 / uint16) on a CUDA device, or
+                 on the host (staged through the current GPU);
+    output_size  ``(h, w)``; ``None`` keeps the size (pure offset correction);
+    offset       ``(x, y)`` in texels of ``frames``: the ``.offset`` a ``prescale()`` result carries;
+    kernel       'bilinear', 'catmull_rom', 'mitchell', 'spline36' or 'lanczos' (mpv's filter kernels, not widened when
+                 downscaling, which is mpv's default).
+
+    Output pixel o of an axis samples the input at ``(o + 0.5) * in / out - 0.5 + offset`` (clamp-to-edge)."""
+    if kernel not in _native.SCALERS:
+        raise ValueError(f"kernel must be one of {sorted(_native.SCALERS)}")
+    if not isinstance(frames, torch.Tensor) or frames.dtype not in _FMT_OF:
+        raise TypeError("frames must be a float32 / float16 / uint8 / uint16 torch.Tensor")
+    if frames.dim() not in (2, 3, 4):
+        raise ValueError(f"expected [H,W], [N,H,W] or [N,C,H,W]; got {tuple(frames.shape)}")
+    if not torch.cuda.is_available():
+        raise _native.NativeError("resample() needs a CUDA device: there is no CPU fallback")
+    host = frames.device.type != "cuda"
+    dev = torch.device("cuda", torch.cuda.current_device()) if host else frames.device
+    x = frames.to(dev, non_blocking=True) if host else frames
+    h, w = x.shape[-2], x.shape[-1]
+    if h < 1 or w < 1:
+        raise ValueError("empty plane")
+    lead = tuple(x.shape[:-2])
+    x3 = x.reshape((-1, h, w))
+    if not (x3.stride(2) == 1 and x3.stride(1) >= w):
+        x3 = x3.contiguous()
+    oh, ow = (h, w) if output_size is None else (int(output_size[0]), int(output_size[1]))
+    io = PlaneIO(x3.dtype, out_dtype, bit_depth, out_bit_depth)
+    outp = torch.empty((x3.shape[0], oh, ow), dtype=io.out_dtype, device=dev)
+    iod = io.desc()
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = _native.lib().mpvp_resample_launch_io(
+            dev.index, _native.SCALERS[kernel], x3.data_ptr(), outp.data_ptr(), x3.shape[0], h, w, oh, ow,
+            float(offset[0]), float(offset[1]), x3.stride(0), x3.stride(1), outp.stride(0), outp.stride(1),
+            ctypes.byref(iod), stream)
+    _native.check(rc, "mpvp_resample_launch_io")
+    res = outp.reshape(lead + (oh, ow))
+    return res.cpu() if host else res
 
 
 _host_streams: Dict[int, List[torch.cuda.Stream]] = {}
