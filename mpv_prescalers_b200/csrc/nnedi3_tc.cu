@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpvp {
 namespace {
@@ -157,8 +158,12 @@ __device__ __forceinline__ float rcp_newton(float u) {
   return r;
 }
 
-template <int S, int DIR, int NNS, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_constant__ NnTcArgs A) {
+// TMA: the source window of a tile (32 x 4 pixels + halo) arrives by cp.async.bulk.tensor into the warpgroup's staging
+// buffer (float32 planes that meet the 16-byte rules, tma.cuh): one elected thread per warpgroup issues the box of the
+// NEXT tile while the current tile's epilogue runs, completion on a per-warpgroup mbarrier; the box starts 4 texels left
+// of the tile (16-byte aligned origin) and is 40 texels wide; border tiles are patched to clamp-to-edge after arrival.
+template <int S, int DIR, int NNS, int EPI, bool TMA>
+__global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_constant__ NnTcArgs A, const __grid_constant__ CUtensorMap tmap) {
   constexpr int K = 8 * S;                  // window samples
   constexpr int KX = K + 16;                // + one MMA K-step carrying the biases
   constexpr int KC = K / 8;                 // 16-byte K chunks written per tile
@@ -173,8 +178,10 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   constexpr int NA = DB ? 2 : 1;            // A buffers per warpgroup
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
-  constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
-  constexpr int STG = (SW * SH + 3) & ~3;
+  constexpr int XO = TMA ? 4 : OX;                         // staged columns left of the tile
+  constexpr int SW = TMA ? 40 : (kTileW + HX - 1), SH = kTileH + HY - 1;
+  static_assert(!TMA || (4 + kTileW + HX - 1 - OX) <= 40, "TMA box too narrow");
+  constexpr int STG = (SW * SH + 31) & ~31;                // floats per staging buffer (128-byte multiple)
   constexpr uint32_t kBBytes = (uint32_t)KX * N * 2;
   constexpr uint32_t kABytes = (uint32_t)KX * 128 * 2;
 
@@ -182,8 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   unsigned char* s_b = smem;                               // B operand
   unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
   float* s_stage = reinterpret_cast<float*>(s_a + kWG * NA * kABytes);  // [kWG][STG]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] + 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 2 * kWG + 1);
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] MMA done, + 1 (B operand), + [kWG] staging
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 3 * kWG + 1);
 
   const int tid = threadIdx.x;
   const int wg = tid >> 7;       // warpgroup
@@ -195,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   if (tid == 0) {
     for (int i = 0; i < 2 * kWG; ++i) mbar_init(smem_u32(s_mbar + i), 1);
     mbar_init(mbar_b, 1);
+    for (int i = 0; i < kWG; ++i) mbar_init(smem_u32(s_mbar + 2 * kWG + 1 + i), 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
@@ -229,6 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
   const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
+  const uint32_t stage_bar = smem_u32(s_mbar + 2 * kWG + 1 + wg);
+  uint32_t stage_phase = 0;   // parity of this warpgroup's staging barrier (TMA)
+  const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
 
   auto issue_chunk = [&](int c, int slot = 0) {
     // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T   (slot: A buffer / TMEM slot / mbarrier of the DB mode)
@@ -247,6 +258,14 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     if (tile >= A.total_tiles) return;
     const int f = tw.f;
     const int x0 = tw.tix * kTileW, y0 = tw.tiy * kTileH;
+    if constexpr (TMA) {
+      if (lt == 0) {
+        fence_proxy_async();   // the warpgroup's reads of the buffer (ordered by its barrier) precede the async write
+        tma_expect(stage_bar, SW * SH * 4);
+        tma_load_3d(smem_u32(my_stage), tmap_ptr, x0 - XO, y0 - OY, f, stage_bar);
+      }
+      return;
+    }
     const int64_t src0 = (int64_t)f * A.in_sn;
     for (int i = lt; i < SW * SH; i += 128) {
       const int sy = i / SW, sx = i - sy * SW;
@@ -275,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
       for (int e = 0; e < 2; ++e) {
         const int a = (k + e) / S, b = (k + e) % S;
         const int dx = DIR == 0 ? a : b, dy = DIR == 0 ? b : a;
-        v[e] = my_stage[(ty + dy) * SW + tx + dx];
+        v[e] = my_stage[(ty + dy) * SW + tx + dx + (XO - OX)];
       }
       xs[k / 2] = make_float2(v[0], v[1]);
       sum2 = __fadd2_rn(sum2, xs[k / 2]);
@@ -324,8 +343,16 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     tc.y0 = ahead.tiy * kTileH;
     ahead.next();
 
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    wg_barrier(wg);  // the staged window of this tile is complete and visible
+    if constexpr (TMA) {
+      mbar_wait(stage_bar, stage_phase);   // every thread waits: the box has landed and is visible
+      stage_phase ^= 1;
+      const bool edge = tc.x0 - XO < 0 || tc.y0 - OY < 0 || tc.x0 - XO + SW > A.w || tc.y0 - OY + SH > A.h;
+      if (edge)   // warpgroup-uniform: replicate the border over the zero-filled texels
+        patch_clamp_to_edge(my_stage, SW, SW, SH, tc.x0 - XO, tc.y0 - OY, A.w, A.h, lt, 128, [&] { wg_barrier(wg); });
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      wg_barrier(wg);  // the staged window of this tile is complete and visible
+    }
 
     // ---- im2col + normalisation -> A operand ----------------------------------------------------
     build_a(my_a + slot * kABytes, tc.mstd0, tc.mstd1, tc.orig);
@@ -508,10 +535,14 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   MPVP_REQUIRE(a0.group == 16, "NNEDI3 weights were packed with %d neurons per accumulator block, the kernel expects 16", a0.group);
   constexpr int K = 8 * S, KX = K + 16, N = 2 * NNS;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
-  constexpr int SW = kTileW + HX - 1, SH = kTileH + HY - 1;
-  constexpr int STG = (SW * SH + 3) & ~3;
+  constexpr int SH = kTileH + HY - 1;
   constexpr int NA = (N <= 64) ? 2 : 1;  // A buffers per warpgroup (two tiles in flight for nns16 / nns32)
-  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * NA * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (2 * kWG + 1) + 16;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const bool use_tma = a0.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&tmap, a0.in, 4, a0.w, a0.h, a0.n, a0.in_sy, a0.in_sn, 40, SH);
+  const int SW = use_tma ? 40 : (kTileW + HX - 1);
+  const int STG = (SW * SH + 31) & ~31;
+  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * NA * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (3 * kWG + 1) + 16;
   // one CTA per SM: the kernel allocates all 512 TMEM columns
   if (smem < 120 * 1024) smem = 120 * 1024;
   NnTcArgs a = a0;
@@ -520,17 +551,19 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
   MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
   const int mode = epi_mode();
-  auto kern = mode == 0 ? nnedi3_tc_kernel<S, DIR, NNS, 0>
-              : mode == 1 ? nnedi3_tc_kernel<S, DIR, NNS, 1>
-              : mode == 2 ? nnedi3_tc_kernel<S, DIR, NNS, 2>
-                          : nnedi3_tc_kernel<S, DIR, NNS, 3>;
+  auto kern = use_tma ? nnedi3_tc_kernel<S, DIR, NNS, 3, true> : nnedi3_tc_kernel<S, DIR, NNS, 3, false>;
+  if (mode != 3) {   // A/B epilogue variants run on the plain-load staging path
+    kern = mode == 0 ? nnedi3_tc_kernel<S, DIR, NNS, 0, false>
+           : mode == 1 ? nnedi3_tc_kernel<S, DIR, NNS, 1, false>
+                       : nnedi3_tc_kernel<S, DIR, NNS, 2, false>;
+  }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = sm_count(device);
   const long long need = (a.total_tiles + kWG - 1) / kWG;
   if (grid > need) grid = need;
   grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(a, tmap);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;

@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpvp {
 namespace {
@@ -123,25 +124,53 @@ __device__ __forceinline__ void ravu_apply(int row, const void* __restrict__ s_l
 
 // KEYMODE: 0 luma (C=1), 1 yuv (key = channel 0), 2 rgb (key = BT.709 luma)
 // OF32: float32 output planes at compile time (the common case; false = any mpvp_io output format)
-template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32>
-__global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A) {
+// TMA: the HOOKED tile + halo arrives by cp.async.bulk.tensor (float32 planes that meet the 16-byte rules, tma.cuh): the
+// box starts XO = 4 / 8 texels left of the tile (16-byte aligned origin) and is 72 / 80 texels wide; luma kernels keep two
+// tile buffers so that the next tile is in flight while the current one is computed (three-channel tiles fill shared
+// memory: one buffer, issue and wait); border tiles are patched to clamp-to-edge after arrival.
+template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32, bool TMA>
+__global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A, const __grid_constant__ CUtensorMap tmap) {
   constexpr int N = 2 * R, TAPS = N * N;
   constexpr int kTH = TileH<C>::v;
   constexpr int LW = (TAPS / 2 + 3) / 4;
   constexpr int LWP = LW | 1;
   constexpr int HH = 2 * R - 1;              // HOOKED halo
-  constexpr int HW_ = kTW + 2 * HH, HHt = kTH + 2 * HH;   // staged HOOKED tile
+  constexpr int XO = TMA ? ((HH + 3) & ~3) : HH;          // staged columns left of the tile
+  constexpr int HW_ = TMA ? ((XO + kTW + HH + 3) & ~3) : (kTW + 2 * HH), HHt = kTH + 2 * HH;   // staged HOOKED tile
+#ifndef MPVP_X_RAVU_NBUF_R4
+#define MPVP_X_RAVU_NBUF_R4 1   // r4 luma: one buffer (the second buffer's per-iteration base costs more than the overlap wins: 3.29 vs 2.87 ms per 16 frames)
+#endif
+  constexpr int NBUF = (TMA && C == 1) ? (R == 4 ? MPVP_X_RAVU_NBUF_R4 : 2) : 1;
+  constexpr int HPL = TMA ? ((HHt * HW_ + 31) & ~31) : HHt * HW_;   // plane pitch (TMA destinations are 128-byte aligned)
   constexpr int IW = kTW + 2 * R - 1, IH = kTH + 2 * R - 1;  // int11 tile: x' in [x0-R, x0+TW+R-2]
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);  // planes: colours (+ key plane for rgb)
   constexpr int KP = (C == 1) ? 0 : ((KEYMODE == 2) ? 3 : 0);  // index of the key plane
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_lut = reinterpret_cast<float4*>(smem_raw);
   constexpr int kLutBytes = (int)(LH ? sizeof(uint2) : sizeof(float4)) * 648 * LWP;
-  float* s_h = reinterpret_cast<float*>(smem_raw + ((kLutBytes + 15) & ~15));  // [NP][HHt][HW_]
-  float* s_i = s_h + NP * HHt * HW_;                                             // [NP][IH][IW]
+  constexpr int HBUF = (NP * HPL + 31) & ~31;                              // floats per HOOKED buffer (128-byte multiple)
+  float* s_h0 = reinterpret_cast<float*>(smem_raw + ((kLutBytes + 127) & ~127));  // [NBUF][NP][HHt][HW_]
+  float* s_i = s_h0 + NBUF * HBUF;                                               // [NP][IH][IW]
+  __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init1(smem_addr(&s_mbar[0]));
+      mbar_init1(smem_addr(&s_mbar[1]));
+      mbar_init_fence();
+    }
+  }
+  const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
+  // one thread asks the TMA engine for the colour planes of a tile (plane index = frame * C + channel)
+  auto tma_issue = [&, tmap_ptr](const TileWalk& tw, int buf) {
+    const uint32_t bar = smem_addr(&s_mbar[buf]);
+    tma_expect(bar, C * HHt * HW_ * 4);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      tma_load_3d(smem_addr(s_h0 + buf * HBUF + c * HPL), tmap_ptr, tw.tix * kTW - XO, tw.tiy * kTH - HH, tw.f * C + c, bar);
+  };
   if constexpr (LH) {
     for (int i = tid; i < 648 * LW; i += NT) reinterpret_cast<uint2*>(smem_raw)[(i / LW) * LWP + (i % LW)] = A.lut_half[i];
   } else {
@@ -149,18 +178,53 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
   }
 
   TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next()) {
+  TileWalk ahead = walk;
+  __syncthreads();   // LUT and mbarriers are set up
+  if constexpr (TMA && NBUF == 2) {
+    if (tid < 32 && blockIdx.x < A.total_tiles) {
+      if (elect_one()) tma_issue(ahead, 0);
+    }
+  }
+  ahead.next();
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next(), ahead.next(), ++it) {
     const int tix = walk.tix, tiy = walk.tiy, f = walk.f;
     const int x0 = tix * kTW, y0 = tiy * kTH;
     const int64_t src0 = (int64_t)f * A.in_sn;
+    float* __restrict__ s_h = s_h0 + (NBUF == 2 ? (it & 1) * HBUF : 0);
 
-    __syncthreads();
+    __syncthreads();   // previous tile fully consumed (its HOOKED buffer and the int11 tile are free)
+    if constexpr (TMA) {
+      if constexpr (NBUF == 2) {
+        if (tid < 32 && tile + gridDim.x < A.total_tiles) {
+          fence_proxy_async_smem();
+          if (elect_one()) tma_issue(ahead, (it + 1) & 1);
+        }
+        mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
+      } else {
+        if (tid < 32) {
+          fence_proxy_async_smem();
+          if (elect_one()) tma_issue(walk, 0);
+        }
+        mbar_wait_parity(smem_addr(&s_mbar[0]), it & 1);
+      }
+      const bool edge = x0 - XO < 0 || y0 - HH < 0 || x0 - XO + HW_ > A.w || y0 - HH + HHt > A.h;
+      if (edge) {   // CTA-uniform
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          patch_clamp_to_edge(s_h + c * HPL, HW_, HW_, HHt, x0 - XO, y0 - HH, A.w, A.h, tid, NT, [] { __syncthreads(); });
+      }
+      if constexpr (KEYMODE == 2) {
+        for (int i = tid; i < HW_ * HHt; i += NT)
+          s_h[3 * HPL + i] = rgb_luma(s_h[i], s_h[HPL + i], s_h[2 * HPL + i]);
+      }
+    } else {
     // ---- stage HOOKED (clamp-to-edge) ---------------------------------------------------
     dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
       constexpr int FMT = decltype(ftag)::value;
       for (int i = tid; i < HW_ * HHt; i += NT) {
         const int sy = i / HW_, sx = i - sy * HW_;
-        const int gx = clampi(x0 + sx - HH, 0, A.w - 1);
+        const int gx = clampi(x0 + sx - XO, 0, A.w - 1);
         const int gy = clampi(y0 + sy - HH, 0, A.h - 1);
         const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
         if (C == 1) {
@@ -170,12 +234,13 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
           const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
           const float c2 = load_px_t<FMT>(A.in, off + 2 * A.in_sc, A.io.in_max);
           s_h[i] = c0;
-          s_h[HHt * HW_ + i] = c1;
-          s_h[2 * HHt * HW_ + i] = c2;
-          if (KEYMODE == 2) s_h[3 * HHt * HW_ + i] = rgb_luma(c0, c1, c2);
+          s_h[HPL + i] = c1;
+          s_h[2 * HPL + i] = c2;
+          if (KEYMODE == 2) s_h[3 * HPL + i] = rgb_luma(c0, c1, c2);
         }
       }
     });
+    }
     __syncthreads();
 
     // ---- phase A: int11 on the tile + halo ------------------------------------------------
@@ -184,13 +249,13 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const int px = x0 - R + ix, py = y0 - R + iy;          // int11 texel this slot stands for
       const int cx = clampi(px, 0, A.w - 1), cy = clampi(py, 0, A.h - 1);
       // staged coordinates of the window origin (tap offset -(R-1))
-      const int bx = cx - (R - 1) - (x0 - HH), by = cy - (R - 1) - (y0 - HH);
-      const float* __restrict__ kb = s_h + KP * HHt * HW_ + by * HW_ + bx;
+      const int bx = cx - (R - 1) - (x0 - XO), by = cy - (R - 1) - (y0 - HH);
+      const float* __restrict__ kb = s_h + KP * HPL + by * HW_ + bx;
       const float* __restrict__ cb = s_h + by * HW_ + bx;
       float res[C];
       const int row = ravu_conv<R, C, LH>(
           A.key, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
-          [&](int c, int t) { return cb[c * HHt * HW_ + (t % N) * HW_ + (t / N)]; }, res);
+          [&](int c, int t) { return cb[c * HPL + (t % N) * HW_ + (t / N)]; }, res);
 #pragma unroll
       for (int c = 0; c < C; ++c) s_i[c * IH * IW + i] = res[c];
       if (KEYMODE == 2) s_i[3 * IH * IW + i] = rgb_luma(res[0], res[C > 1 ? 1 : 0], res[C > 2 ? 2 : 0]);
@@ -204,7 +269,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const int ly = i / kTW, lx = i - ly * kTW;
       const int x = x0 + lx, y = y0 + ly;
       if (x >= A.w || y >= A.h) continue;
-      const float* __restrict__ hb = s_h + (ly + HH) * HW_ + (lx + HH);  // HOOKED(x, y)
+      const float* __restrict__ hb = s_h + (ly + HH) * HW_ + (lx + XO);  // HOOKED(x, y)
       const float* __restrict__ ib = s_i + (ly + R) * IW + (lx + R);     // int11(x, y)
       float r10[C], r01[C];
       int rows[2];
@@ -217,7 +282,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       // registers, which the compiler evaluates once.
       auto fetch0 = [&](int plane, int ii, int jj) -> float {
         const int px2 = 1 - (2 * R - 1) + ii + jj, py2 = -ii + jj;
-        if ((px2 & 1) == 0) return hb[plane * HHt * HW_ + (py2 / 2) * HW_ + (px2 / 2)];
+        if ((px2 & 1) == 0) return hb[plane * HPL + (py2 / 2) * HW_ + (px2 / 2)];
         return ib[plane * IH * IW + ((py2 - 1) / 2) * IW + ((px2 - 1) / 2)];
       };
       float U[(N + 1) * N];
@@ -251,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
         const int64_t o = (int64_t)f * A.out_sn + c * A.out_sc + (int64_t)(2 * y) * A.out_sy + 2 * x;
         // (2x,2y)=HOOKED (2x+1,2y)=int10 (2x,2y+1)=int01 (2x+1,2y+1)=int11   (ravu-r2.hook:327-338)
         const int ofmt = OF32 ? MPVP_FMT_F32 : A.io.out_fmt;
-        store_px2(A.out, o, hb[c * HHt * HW_], r10[c], ofmt, A.io.out_max);
+        store_px2(A.out, o, hb[c * HPL], r10[c], ofmt, A.io.out_max);
         store_px2(A.out, o + A.out_sy, r01[c], ib[c * IH * IW], ofmt, A.io.out_max);
       }
     }
@@ -263,14 +328,24 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   constexpr int N = 2 * R, TAPS = N * N, LW = ((TAPS / 2 + 3) / 4) | 1, HH = 2 * R - 1;  // LW: padded pitch
   constexpr int kTH = TileH<C>::v;
   constexpr int NP = (C == 1) ? 1 : ((KEYMODE == 2) ? 4 : 3);
-  const size_t smem = (((LH ? sizeof(uint2) : sizeof(float4)) * 648 * LW + 15) & ~(size_t)15) +
-                      sizeof(float) * NP * ((kTW + 2 * HH) * (kTH + 2 * HH) + (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
+  constexpr int XO_T = (HH + 3) & ~3, HW_T = (XO_T + kTW + HH + 3) & ~3, HHt = kTH + 2 * HH;
   RavuArgs a = a0;
   a.tiles_x = (a.w + kTW - 1) / kTW;
   a.tiles_y = (a.h + kTH - 1) / kTH;
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * a.n;
   MPVP_REQUIRE(a.total_tiles < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", a.total_tiles);
-  auto kern = ravu_kernel<R, C, KEYMODE, NT, LH, OF32>;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  // float32 planes whose channels are evenly spaced (plane index = frame * C + channel) can be fetched by TMA
+  bool use_tma = false;
+  if (a.io.in_fmt == MPVP_FMT_F32 && (C == 1 || a.in_sn == (int64_t)C * a.in_sc))
+    use_tma = make_plane_tmap(&tmap, a.in, 4, a.w, a.h, a.n * C, a.in_sy, C == 1 ? a.in_sn : a.in_sc, HW_T, HHt);
+  const int hw = use_tma ? HW_T : (kTW + 2 * HH), nbuf = (use_tma && C == 1) ? (R == 4 ? MPVP_X_RAVU_NBUF_R4 : 2) : 1;
+  const size_t hpl = use_tma ? (((size_t)HHt * hw + 31) & ~(size_t)31) : (size_t)HHt * hw;
+  const size_t hbuf = (NP * hpl + 31) & ~(size_t)31;
+  const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * 648 * LW) + 127) & ~(size_t)127) +
+                      sizeof(float) * (nbuf * hbuf + (size_t)NP * (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
+  auto kern = use_tma ? ravu_kernel<R, C, KEYMODE, NT, LH, OF32, true> : ravu_kernel<R, C, KEYMODE, NT, LH, OF32, false>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -282,7 +357,7 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   if (grid > a.total_tiles) grid = a.total_tiles;
   grid = cap_grid(grid);
   if (grid < 1) return MPVP_OK;
-  kern<<<(unsigned)grid, NT, smem, stream>>>(a);
+  kern<<<(unsigned)grid, NT, smem, stream>>>(a, tmap);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MPVP_CUDA_OK(cudaGetLastError());
   return MPVP_OK;

@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpvp {
 
@@ -105,34 +106,6 @@ __device__ __forceinline__ float rgb_luma709(float r, float g, float b) {
 }
 
 // C = colour channels (1 or 3; 3 only for SCALE == 3), KEYMODE: 0 luma, 1 yuv (key = channel 0), 2 rgb
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait_parity(uint32_t addr, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
-
-// true for exactly one lane of a fully converged warp (elect.sync)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // LH: LUT kept in shared memory as 4 x binary16 per texel (exact: the texels ARE binary16 values, App. D.1).  A warp's
 // 32 lanes gather 32 different LUT rows, so the gather is bank-conflict bound: 8-byte texels need half the
 // shared-memory wavefronts of 16-byte ones (68 vs 133 per 13-texel row on the config-2 planes).
@@ -462,48 +435,6 @@ ravu_lite_kernel(const __grid_constant__ LiteArgs A, const __grid_constant__ CUt
       __syncthreads();
     }
   }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// MPVP_TMA=0 forces the plain-load staging path (A/B switch)
-bool tma_enabled() {
-  static const bool v = [] {
-    const char* e = getenv("MPVP_TMA");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
-// 3-D tensor map {w, h, n} over the input planes with a (box_w x box_h x 1) box; false if the layout does not
-// meet TMA's 16-byte rules (then the kernel stages with plain loads)
-bool make_plane_tmap(CUtensorMap* tm, const void* base, int eb, int w, int h, int n, int64_t sy, int64_t sn, int box_w, int box_h) {
-  if (!tma_enabled() || !encode_tiled()) return false;
-  if (n == 1) sn = (int64_t)h * sy;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (sy * eb) % 16 || (sn * eb) % 16 || sy < w || box_w > 256 || box_h > 256 ||
-      (box_w * eb) % 16)
-    return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  const cuuint64_t strides[2] = {(cuuint64_t)sy * eb, (cuuint64_t)sn * eb};
-  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapDataType dt = eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
-  return encode_tiled()(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int R, bool AR, int SCALE, int P, int STRIPS, int C, int KEYMODE, bool FASTKEY, bool LH, bool OF32>

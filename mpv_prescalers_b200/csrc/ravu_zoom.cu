@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpvp {
 namespace {
@@ -389,19 +390,55 @@ constexpr float kMaxSpread = 2.6e-4f;             // ... whose total spread must
 
 // ---- key pre-pass: LUT row of every source cell (base texel (x-1, y-1), x in [0, w], y in [0, h]) -------------------
 constexpr int kKTW = 64, kKTH = 16;
-template <int R, int C, int KEYMODE>
-__global__ void __launch_bounds__(256) zoom_key_kernel(const __grid_constant__ ZoomArgs A) {
+// TMA (luma float32 planes): the window tile arrives by cp.async.bulk.tensor into a double buffer, the next tile in flight
+// while the keys of the current one are computed; the box starts 4 texels left of the first cell (16-byte aligned origin).
+template <int R, int C, int KEYMODE, bool TMA>
+__global__ void __launch_bounds__(256) zoom_key_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
   constexpr int N = 2 * R, TAPS = N * N, G = 4;
-  constexpr int SW = kKTW + N - 1, SH = kKTH + N - 1;
-  __shared__ float s_k[SW * SH];
+  constexpr int XO = TMA ? 4 : R;   // staged columns left of the first cell's base texel + 1
+  constexpr int SW = TMA ? 72 : (kKTW + N - 1), SH = kKTH + N - 1;
+  static_assert(!TMA || (4 + kKTW - 1 + R) <= 72, "TMA box too narrow");
+  constexpr int KBUF = (SW * SH + 31) & ~31;
+  __shared__ __align__(128) float s_kb[(TMA ? 2 : 1) * KBUF];
+  __shared__ __align__(8) uint64_t s_mbar[2];
   const int tid = threadIdx.x;
   const int cw = A.w + 1, ch = A.h + 1;
+  const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
+  auto tma_issue = [&, tmap_ptr](const TileWalk& tw, int buf) {
+    const uint32_t bar = smem_addr(&s_mbar[buf]);
+    tma_expect(bar, SW * SH * 4);
+    tma_load_3d(smem_addr(s_kb + buf * KBUF), tmap_ptr, tw.tix * kKTW - XO, tw.tiy * kKTH - R, tw.f, bar);
+  };
   TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
-  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next()) {
+  TileWalk ahead = walk;
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init1(smem_addr(&s_mbar[0]));
+      mbar_init1(smem_addr(&s_mbar[1]));
+      mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid < 32 && blockIdx.x < A.total_tiles) {
+      if (elect_one()) tma_issue(ahead, 0);
+    }
+  }
+  ahead.next();
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next(), ahead.next(), ++it) {
     const int f = walk.f;
     const int cx0 = walk.tix * kKTW, cy0 = walk.tiy * kKTH;   // cell tile origin (cell index = base + 1)
     const int64_t src0 = (int64_t)f * A.in_sn;
-    __syncthreads();
+    float* __restrict__ s_k = s_kb + (TMA ? (it & 1) * KBUF : 0);
+    __syncthreads();   // the previous tile's keys are done: its buffer (the one `ahead` lands in) is free
+    if constexpr (TMA) {
+      if (tid < 32 && tile + gridDim.x < A.total_tiles) {
+        fence_proxy_async_smem();
+        if (elect_one()) tma_issue(ahead, (it + 1) & 1);
+      }
+      mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
+      const bool edge = cx0 - XO < 0 || cy0 - R < 0 || cx0 - XO + SW > A.w || cy0 - R + SH > A.h;
+      if (edge) patch_clamp_to_edge(s_k, SW, SW, SH, cx0 - XO, cy0 - R, A.w, A.h, tid, 256, [] { __syncthreads(); });
+    } else {
     dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
       constexpr int FMT = decltype(ftag)::value;
       for (int i = tid; i < SW * SH; i += 256) {
@@ -420,11 +457,12 @@ __global__ void __launch_bounds__(256) zoom_key_kernel(const __grid_constant__ Z
       }
     });
     __syncthreads();
+    }
     for (int i = tid; i < kKTW * kKTH; i += 256) {
       const int ly = i / kKTW, lx = i - ly * kKTW;
       const int cx = cx0 + lx, cy = cy0 + ly;
       if (cx >= cw || cy >= ch) continue;
-      const float* __restrict__ kb = s_k + ly * SW + lx;
+      const float* __restrict__ kb = s_k + ly * SW + lx + (XO - R);
       float ks[TAPS];
 #pragma unroll
       for (int t = 0; t < TAPS; ++t) ks[t] = kb[(t % N) * SW + (t / N)];
@@ -506,14 +544,17 @@ __device__ __forceinline__ void store_px_wb(void* __restrict__ p, int64_t off, f
 }
 
 // SWT: compile-time pitch of the staged source tile (0 = runtime A.sw): immediate offsets for the window loads.
+// TMA (luma float32 planes, SWT > 0): the source tile arrives by cp.async.bulk.tensor; its box starts at the 16-byte
+// aligned texel at or left of the tile's first texel (the window offsets absorb the 0..3 texel difference).
 // STRIP: member rows per thread (the CTA has kPTW * kPTH / STRIP threads).
 #ifndef MPVP_X_ZOOM_STRIP
 #define MPVP_X_ZOOM_STRIP 4
 #endif
 constexpr int kStrip = MPVP_X_ZOOM_STRIP;
 constexpr int kPNT2 = kPTW * kPTH / kStrip;
-template <int R, int C, bool AR, int SWT, bool MIX>
-__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A) {
+template <int R, int C, bool AR, int SWT, bool MIX, bool TMA = false>
+__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(!TMA || (C == 1 && !AR && SWT > 0), "TMA staging: luma, no anti-ringing power tile, compile-time pitch");
   constexpr int kPNT = kPNT2;
   constexpr int N = 2 * R, TAPS = N * N;
   using PG = PhaseGeom<R, AR, MIX>;
@@ -522,13 +563,21 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3)
   constexpr int STRIP = kStrip;
   static_assert(!MIX || !AR, "the anti-ringing weights stay float32");
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_lut = reinterpret_cast<float*>(smem_raw);            // [288][PITCH]
   float* s_src = s_lut + 288 * PITCH;                           // [C][sh][sw]
   float4* s_pow = reinterpret_cast<float4*>(s_src + (((size_t)C * A.sh * A.sw + 3) & ~(size_t)3));   // [sh][sw] (POWT)
   __shared__ int s_mxo[kPTW], s_mxb[kPTW], s_myo[kPTH], s_myb[kPTH];
+  __shared__ __align__(8) uint64_t s_mbar;
 
   const int tid = threadIdx.x;
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init1(smem_addr(&s_mbar));
+      mbar_init_fence();
+    }
+  }
+  uint32_t tma_phase = 0;
   const int SW = SWT ? SWT : A.sw;
   const int PLANE = SW * A.sh;
   const int cw = A.w + 1, ch = A.h + 1;
@@ -583,11 +632,29 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3)
       s_myo[j] = A.yo[m];
       s_myb[j] = A.yb[m];
     }
-    const int xb_first = A.xb[mx0], xb_last = A.xb[mx0 + nmx - 1];
+    const int xb_true = A.xb[mx0], xb_last = A.xb[mx0 + nmx - 1];
     const int yb_first = A.yb[my0], yb_last = A.yb[my0 + nmy - 1];
-    const int sx0 = xb_first - (R - 1), sy0 = yb_first - (R - 1);
+    // TMA: the staged tile starts at the aligned texel ax0 <= xb_true - (R-1); in terms of the window arithmetic below
+    // that is a tile whose "first base" is ax0 + (R-1)
+    const int ax0 = TMA ? ((xb_true - (R - 1)) & ~3) : (xb_true - (R - 1));
+    const int xb_first = ax0 + (R - 1);
+    const int sx0 = ax0, sy0 = yb_first - (R - 1);
     const int need_w = xb_last - xb_first + N, need_h = yb_last - yb_first + N;   // <= sw, sh by construction of the plan
     const int64_t src0 = (int64_t)f * A.in_sn;
+    if constexpr (TMA) {
+      if (tid < 32) {
+        fence_proxy_async_smem();
+        if (elect_one()) {
+          const uint32_t bar = smem_addr(&s_mbar);
+          tma_expect(bar, SWT * A.sh * 4);
+          tma_load_3d(smem_addr(s_src), reinterpret_cast<uint64_t>(&tmap), sx0, sy0, f, bar);
+        }
+      }
+      mbar_wait_parity(smem_addr(&s_mbar), tma_phase);
+      tma_phase ^= 1;
+      const bool edge = sx0 < 0 || sy0 < 0 || sx0 + SWT > A.w || sy0 + A.sh > A.h;
+      if (edge) patch_clamp_to_edge(s_src, SWT, SWT, A.sh, sx0, sy0, A.w, A.h, tid, kPNT, [] { __syncthreads(); });
+    } else
     dispatch_in_fmt(A.io.in_fmt, [&](auto ftag) {
       constexpr int FMT = decltype(ftag)::value;
       for (int i = tid; i < need_w * need_h; i += kPNT) {
@@ -957,22 +1024,33 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
     k.tiles_x = (a.w + 1 + kKTW - 1) / kKTW;
     k.tiles_y = (a.h + 1 + kKTH - 1) / kKTH;
     k.total_tiles = (long long)k.tiles_x * k.tiles_y * a.n;
-    auto kern = zoom_key_kernel<R, C, KEYMODE>;
+    alignas(64) CUtensorMap ktm;
+    memset(&ktm, 0, sizeof(ktm));
+    bool ktma = false;
+    if constexpr (C == 1) ktma = a.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&ktm, a.in, 4, a.w, a.h, a.n, a.in_sy, a.in_sn, 72, kKTH + 2 * R - 1);
+    auto kern = ktma ? zoom_key_kernel<R, C, KEYMODE, C == 1> : zoom_key_kernel<R, C, KEYMODE, false>;
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
     long long grid = (long long)sm_count(device) * (per_sm < 1 ? 1 : per_sm);
     if (grid > k.total_tiles) grid = k.total_tiles;
     grid = cap_grid(grid);
-    kern<<<(unsigned)grid, 256, 0, stream>>>(k);
+    kern<<<(unsigned)grid, 256, 0, stream>>>(k, ktm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   {
     a.total_tiles = total;
     // MPVP_ZOOM_MIX=0: all phase-LUT weights stay float32 in shared memory (A/B switch for the binary16 outer taps)
     const bool mix = !AR && env_flag("MPVP_ZOOM_MIX", true);
-    constexpr int kSWT = kPTW + 2 * R + 3;   // compile-time tile pitch (odd) when neighbouring members sit one texel apart
-    const bool fixed_pitch = a.sw <= kSWT;
+    // compile-time tile pitch when neighbouring members sit one texel apart: tile + window + up to 3 texels of slack for
+    // the 16-byte aligned TMA origin, a multiple of 4 texels (TMA box rows are multiples of 16 bytes)
+    constexpr int kSWT = (kPTW + 2 * R + 3 + 3) & ~3;
+    const bool fixed_pitch = a.sw + 3 <= kSWT;
     if (fixed_pitch) a.sw = kSWT;
+    alignas(64) CUtensorMap ptm;
+    memset(&ptm, 0, sizeof(ptm));
+    bool ptma = false;
+    if constexpr (C == 1 && !AR)
+      ptma = fixed_pitch && a.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&ptm, a.in, 4, a.w, a.h, a.n, a.in_sy, a.in_sn, kSWT, a.sh);
     auto launch = [&](auto kern, int pitch) {
       const size_t smem = sizeof(float) * (288 * (size_t)pitch + (((size_t)C * a.sw * a.sh + 3) & ~(size_t)3)) +
                           ((AR && C == 1) ? sizeof(float4) * (size_t)a.sw * a.sh : 0);
@@ -987,17 +1065,23 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
       long long grid = (long long)sm_count(device) * per_sm;
       if (grid > total) grid = total;
       grid = cap_grid(grid);
-      kern<<<(unsigned)grid, kPNT2, smem, stream>>>(a);
+      kern<<<(unsigned)grid, kPNT2, smem, stream>>>(a, ptm);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     };
     if constexpr (AR) {
       if (fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, false>, PhaseGeom<R, AR, false>::PITCH);
       else launch(zoom_phase_kernel<R, C, AR, 0, false>, PhaseGeom<R, AR, false>::PITCH);
     } else {
-      if (mix && fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, true>, PhaseGeom<R, AR, true>::PITCH);
-      else if (mix) launch(zoom_phase_kernel<R, C, AR, 0, true>, PhaseGeom<R, AR, true>::PITCH);
-      else if (fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, false>, PhaseGeom<R, AR, false>::PITCH);
-      else launch(zoom_phase_kernel<R, C, AR, 0, false>, PhaseGeom<R, AR, false>::PITCH);
+      if constexpr (C == 1) {
+        if (ptma && mix) launch(zoom_phase_kernel<R, C, AR, kSWT, true, true>, PhaseGeom<R, AR, true>::PITCH);
+        else if (ptma) launch(zoom_phase_kernel<R, C, AR, kSWT, false, true>, PhaseGeom<R, AR, false>::PITCH);
+      }
+      if (!ptma) {
+        if (mix && fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, true>, PhaseGeom<R, AR, true>::PITCH);
+        else if (mix) launch(zoom_phase_kernel<R, C, AR, 0, true>, PhaseGeom<R, AR, true>::PITCH);
+        else if (fixed_pitch) launch(zoom_phase_kernel<R, C, AR, kSWT, false>, PhaseGeom<R, AR, false>::PITCH);
+        else launch(zoom_phase_kernel<R, C, AR, 0, false>, PhaseGeom<R, AR, false>::PITCH);
+      }
     }
   }
   e = cudaGetLastError();
