@@ -175,7 +175,14 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   // two mbarriers), so the build -> MMA -> epilogue latency chain of a tile, which dominates when the epilogue is
   // only 16-32 neurons long, overlaps the neighbouring tile's work.
   constexpr bool DB = (NCH == 1 && CN <= 64);
-  constexpr int NA = DB ? 2 : 1;            // A buffers per warpgroup
+  // Larger networks pipeline ACROSS tiles instead (XT): the A operand of tile t+1 is built (second A buffer) while the MMA of
+  // tile t's last chunk runs, and its first MMA is issued at the barrier that ends tile t's last TMEM read -- the
+  // stage-wait -> build -> barrier -> MMA -> wait chain of a tile's start is off the warpgroup's critical path.
+#ifndef MPVP_X_NN_XT
+#define MPVP_X_NN_XT 0   // measured slower: nns256-win8x6 4.89 vs 4.69 ms, nns128-win8x4 2.64 vs 2.51 ms (kept as an A/B knob)
+#endif
+  constexpr bool XT = !DB && MPVP_X_NN_XT;
+  constexpr int NA = (DB || XT) ? 2 : 1;    // A buffers per warpgroup
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int OX = DIR == 0 ? 3 : (S / 2 - 1), OY = DIR == 0 ? (S / 2 - 1) : 3;
   constexpr int XO = TMA ? 4 : OX;                         // staged columns left of the tile
@@ -241,11 +248,13 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   uint32_t stage_phase = 0;   // parity of this warpgroup's staging barrier (TMA)
   const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
 
-  auto issue_chunk = [&](int c, int slot = 0) {
-    // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T   (slot: A buffer / TMEM slot / mbarrier of the DB mode)
+  auto issue_chunk = [&](int c, int slot = 0, int aslot = -1) {
+    // D[128 x CN] = A[128 x KX] . B[rows c*CN .. c*CN+CN-1]^T   (slot: TMEM slot / mbarrier of the DB mode; aslot: A buffer,
+    // = slot unless given)
+    if (aslot < 0) aslot = slot;
 #pragma unroll
     for (int j = 0; j < KX / 16; ++j) {
-      const uint64_t ad = make_desc(a_addr + slot * kABytes + j * 2 * (128 * 16), 128 * 16, 128);
+      const uint64_t ad = make_desc(a_addr + aslot * kABytes + j * 2 * (128 * 16), 128 * 16, 128);
       const uint64_t bd = make_desc(b_addr + c * CN * 16 + j * 2 * (N * 16), N * 16, 128);
       umma_f16(d_col + (uint32_t)(slot * CN), ad, bd, idesc, j > 0 ? 1u : 0u);
     }
@@ -337,6 +346,24 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   // front half of a tile: staged window -> A operand (buffer `slot`) -> MMA of chunk 0 into TMEM slot `slot`
   // `ahead` always stands one tile beyond the tile whose front half runs (it is the tile being prefetched)
   TileWalk ahead((long long)blockIdx.x * kWG + wg, tile_step, A.tiles_x, A.tiles_y);
+  // XT: staged window -> A operand in buffer `aslot`; no barrier, no MMA (the caller's next barrier publishes A)
+  auto front_build = [&](int aslot, TileCtx& tc) {
+    tc.f = ahead.f;
+    tc.x0 = ahead.tix * kTileW;
+    tc.y0 = ahead.tiy * kTileH;
+    ahead.next();
+    if constexpr (TMA) {
+      mbar_wait(stage_bar, stage_phase);
+      stage_phase ^= 1;
+      const bool edge = tc.x0 - XO < 0 || tc.y0 - OY < 0 || tc.x0 - XO + SW > A.w || tc.y0 - OY + SH > A.h;
+      if (edge) patch_clamp_to_edge(my_stage, SW, SW, SH, tc.x0 - XO, tc.y0 - OY, A.w, A.h, lt, 128, [&] { wg_barrier(wg); });
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      wg_barrier(wg);
+    }
+    build_a(my_a + aslot * kABytes, tc.mstd0, tc.mstd1, tc.orig);
+    fence_proxy_async();
+  };
   auto front = [&](long long tile, int slot, TileCtx& tc) {
     tc.f = ahead.f;
     tc.x0 = ahead.tix * kTileW;
@@ -367,7 +394,9 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   };
 
   // back half: epilogue over the accumulator chunks of the tile (TMEM slot `slot`), then the store
-  auto back = [&](const TileCtx& tc, int slot, uint32_t parity) {
+  // XT: `more` = another tile follows (tile index nxt_tile); its A operand goes to buffer `nxt_aslot`, context to `nxt`
+  auto back = [&](const TileCtx& tc, int slot, uint32_t parity, int aslot = 0, bool more = false, int nxt_aslot = 0,
+                  TileCtx* nxt = nullptr, long long nxt_tile = 0) {
     const float mstd0 = tc.mstd0, mstd1 = tc.mstd1, orig = tc.orig;
     const int x0 = tc.x0, y0 = tc.y0, f = tc.f;
     const uint32_t d_lane_s = d_lane + (uint32_t)(slot * CN);
@@ -376,6 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     float2 wsum2 = make_float2(0.f, 0.f), vsum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
+      if constexpr (XT) {
+        // the MMA of the last chunk is running: build the next tile's A operand under it
+        if (c == NCH - 1 && more) front_build(nxt_aslot, *nxt);
+      }
       if constexpr (DB) {
         mbar_wait(my_mbar + 8u * (uint32_t)slot, parity);
       } else {
@@ -399,8 +432,17 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
           wg_barrier(wg);
           if (lt == 0) {
             tc_fence_after();
-            issue_chunk(c + 1);
+            issue_chunk(c + 1, 0, aslot);
           }
+        } else if (XT && more) {
+          // last block of the tile: the accumulator is free and (same barrier) the next tile's A operand is complete
+          tc_fence_before();
+          wg_barrier(wg);
+          if (lt == 0) {
+            tc_fence_after();
+            issue_chunk(0, 0, nxt_aslot);
+          }
+          prefetch_tile(nxt_tile + tile_step, ahead);   // the staging buffer was last read by front_build above
         }
         // registers 0..15: softmax logits of 16 neurons, 16..31: their elliott inputs
         if constexpr (EPI == 3) {
@@ -503,6 +545,17 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
         if (more) cur = nxt;
       }
     }
+  } else if constexpr (XT) {
+    if (first < A.total_tiles) {
+      TileCtx cur, nxt;
+      front(first, 0, cur);    // first tile: build, barrier, MMA of chunk 0, prefetch of the second tile's window
+      uint32_t it = 0;
+      for (long long tile = first; tile < A.total_tiles; tile += tile_step, ++it) {
+        const bool more = tile + tile_step < A.total_tiles;
+        back(cur, 0, 0, (int)(it & 1), more, (int)((it + 1) & 1), &nxt, tile + tile_step);
+        if (more) cur = nxt;
+      }
+    }
   } else {
     for (long long tile = first; tile < A.total_tiles; tile += tile_step) {
       TileCtx tc;
@@ -536,7 +589,7 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   constexpr int K = 8 * S, KX = K + 16, N = 2 * NNS;
   constexpr int HX = DIR == 0 ? 8 : S, HY = DIR == 0 ? S : 8;
   constexpr int SH = kTileH + HY - 1;
-  constexpr int NA = (N <= 64) ? 2 : 1;  // A buffers per warpgroup (two tiles in flight for nns16 / nns32)
+  constexpr int NA = ((N <= 64) || MPVP_X_NN_XT) ? 2 : 1;  // A buffers per warpgroup (two tiles in flight / cross-tile pipelining)
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   const bool use_tma = a0.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&tmap, a0.in, 4, a0.w, a0.h, a0.n, a0.in_sy, a0.in_sn, 40, SH);
