@@ -128,9 +128,25 @@ __device__ __forceinline__ void ravu_apply(int row, const void* __restrict__ s_l
 // box starts XO = 4 / 8 texels left of the tile (16-byte aligned origin) and is 72 / 80 texels wide; luma kernels keep two
 // tile buffers so that the next tile is in flight while the current one is computed (three-channel tiles fill shared
 // memory: one buffer, issue and wait); border tiles are patched to clamp-to-edge after arrival.
+// GP (r3 / r4 luma): step 1 takes its gradients from per-texel GRADIENT PLANES in shared memory.  A gradient stencil
+// (4th-order where +-2 fits in the window, central at the window's rim; ravu-r4.hook:86-252) depends on the texel and on
+// which of the two forms the window position selects, not on the window itself, so both forms are computed ONCE per
+// texel -- (gx4, gy4) and (gxc, gyc) -- instead of once per window that contains the texel (36 times for r4).  Each
+// value is the same expression on the same samples, so the key sums are bit-identical to the per-window evaluation.
+#ifndef MPVP_X_RAVU_GP
+#define MPVP_X_RAVU_GP 0   // measured: bit-identical, but not faster (ravu-r4 x16: 3.30 vs 2.87 ms at 256 threads, 2.90 at 512; ravu-r3 1.66 vs 1.55): the extra phase + barrier of a 1-CTA/SM kernel costs what the stencils save
+#endif
+template <int R, int C>
+struct UseGP {
+  static constexpr bool v = MPVP_X_RAVU_GP && C == 1 && (R == 3 || R == 4);
+};
 template <int R, int C, int KEYMODE, int NT, bool LH, bool OF32, bool TMA>
 __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ RavuArgs A, const __grid_constant__ CUtensorMap tmap) {
   constexpr int N = 2 * R, TAPS = N * N;
+  constexpr bool GP = UseGP<R, C>::v;
+  constexpr int GG = (R == 4) ? 6 : 4;                       // gradient square side
+  constexpr int GO = (N - GG) / 2;                           // first gradient index in the window (1 for r3 / r4)
+  constexpr int GW = kTW + GG + 2 * R - 2, GH = TileH<C>::v + GG + 2 * R - 2;   // gradient-plane extent (texels)
   constexpr int kTH = TileH<C>::v;
   constexpr int LW = (TAPS / 2 + 3) / 4;
   constexpr int LWP = LW | 1;
@@ -152,6 +168,8 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
   constexpr int HBUF = (NP * HPL + 31) & ~31;                              // floats per HOOKED buffer (128-byte multiple)
   float* s_h0 = reinterpret_cast<float*>(smem_raw + ((kLutBytes + 127) & ~127));  // [NBUF][NP][HHt][HW_]
   float* s_i = s_h0 + NBUF * HBUF;                                               // [NP][IH][IW]
+  float2* s_g4 = reinterpret_cast<float2*>(s_i + ((NP * IH * IW + 3) & ~3));     // [GH][GW] (gx, gy) 4th-order   (GP)
+  float2* s_gc = s_g4 + GW * GH;                                                 // [GH][GW] (gx, gy) central     (GP)
   __shared__ __align__(8) uint64_t s_mbar[2];
 
   const int tid = threadIdx.x;
@@ -243,6 +261,34 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
     }
     __syncthreads();
 
+    // ---- gradient planes of the HOOKED tile (GP) ---------------------------------------------
+    // plane texel (0, 0) is image texel (x0 - (2R-2), y0 - (2R-2)): the first gradient point of the left / top-most window
+    if constexpr (GP) {
+      for (int i = tid; i < GW * GH; i += NT) {
+        const int gy_ = i / GW, gx_ = i - gy_ * GW;
+        // staged coordinates of this texel
+        const int sx = gx_ - (2 * R - 2) + XO, sy = gy_ - (2 * R - 2) + HH;
+        const float* __restrict__ p = s_h + sy * HW_ + sx;
+        float2 g4 = make_float2(0.f, 0.f), gc = g4;
+        // a form whose stencil leaves the staged tile is never selected by any window (it would leave that window too)
+        if (sx >= 2 && sx + 2 < HW_) {
+          float t = __fmaf_rn(8.0f, p[1], -p[2]);
+          t = __fmaf_rn(-8.0f, p[-1], t);
+          g4.x = div12_rn(__fadd_rn(t, p[-2]));
+        }
+        if (sy >= 2 && sy + 2 < HHt) {
+          float t = __fmaf_rn(8.0f, p[HW_], -p[2 * HW_]);
+          t = __fmaf_rn(-8.0f, p[-HW_], t);
+          g4.y = div12_rn(__fadd_rn(t, p[-2 * HW_]));
+        }
+        if (sx >= 1 && sx + 1 < HW_) gc.x = __fmul_rn(__fsub_rn(p[1], p[-1]), 0.5f);
+        if (sy >= 1 && sy + 1 < HHt) gc.y = __fmul_rn(__fsub_rn(p[HW_], p[-HW_]), 0.5f);
+        s_g4[i] = g4;
+        s_gc[i] = gc;
+      }
+      __syncthreads();
+    }
+
     // ---- phase A: int11 on the tile + halo ------------------------------------------------
     for (int i = tid; i < IW * IH; i += NT) {
       const int iy = i / IW, ix = i - iy * IW;
@@ -253,9 +299,38 @@ __global__ void __launch_bounds__(NT, 1) ravu_kernel(const __grid_constant__ Rav
       const float* __restrict__ kb = s_h + KP * HPL + by * HW_ + bx;
       const float* __restrict__ cb = s_h + by * HW_ + bx;
       float res[C];
-      const int row = ravu_conv<R, C, LH>(
-          A.key, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
-          [&](int c, int t) { return cb[c * HPL + (t % N) * HW_ + (t / N)]; }, res);
+      int row;
+      if constexpr (GP) {
+        // window point (i, j) is plane texel (cx - (R-1) + i - (x0 - (2R-2)), ...): same sums, same order as ravu_key2
+        const int qx = cx - x0 + (R - 1), qy = cy - y0 + (R - 1);
+        float2 ad = make_float2(0.0f, 0.0f);
+        float b = 0.0f;
+#pragma unroll
+        for (int ii = GO; ii < GO + GG; ++ii) {
+#pragma unroll
+          for (int jj = GO; jj < GO + GG; ++jj) {
+            const int q = (qy + jj) * GW + qx + ii;
+            const bool x4 = ii - 2 >= 0 && ii + 2 <= N - 1, y4 = jj - 2 >= 0 && jj + 2 <= N - 1;
+            float gx, gy;
+            if (x4 && y4) { const float2 v = s_g4[q]; gx = v.x; gy = v.y; }
+            else if (!x4 && !y4) { const float2 v = s_gc[q]; gx = v.x; gy = v.y; }
+            else { gx = x4 ? s_g4[q].x : s_gc[q].x; gy = y4 ? s_g4[q].y : s_gc[q].y; }
+            const float g = A.key.gauss[(ii - GO) * GG + (jj - GO)];
+            const float2 gxy = make_float2(gx, gy);
+            const float2 t = mul2_rn(mul2_rn(gxy, gxy), make_float2(g, g));
+            ad.x = __fadd_rn(ad.x, t.x);
+            ad.y = __fadd_rn(ad.y, t.y);
+            b = __fadd_rn(b, __fmul_rn(__fmul_rn(gx, gy), g));
+          }
+        }
+        row = key_from_abd_fast<8>(A.key, ad.x, b, ad.y);
+        ravu_apply<R, C, LH>(row, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
+                             [&](int c, int t) { return cb[c * HPL + (t % N) * HW_ + (t / N)]; }, res);
+      } else {
+        row = ravu_conv<R, C, LH>(
+            A.key, s_lut, [&](int t) { return kb[(t % N) * HW_ + (t / N)]; },
+            [&](int c, int t) { return cb[c * HPL + (t % N) * HW_ + (t / N)]; }, res);
+      }
 #pragma unroll
       for (int c = 0; c < C; ++c) s_i[c * IH * IW + i] = res[c];
       if (KEYMODE == 2) s_i[3 * IH * IW + i] = rgb_luma(res[0], res[C > 1 ? 1 : 0], res[C > 2 ? 2 : 0]);
@@ -343,8 +418,10 @@ int launch_ravu_impl(const RavuArgs& a0, int device, cudaStream_t stream) {
   const int hw = use_tma ? HW_T : (kTW + 2 * HH), nbuf = (use_tma && C == 1) ? (R == 4 ? MPVP_X_RAVU_NBUF_R4 : 2) : 1;
   const size_t hpl = use_tma ? (((size_t)HHt * hw + 31) & ~(size_t)31) : (size_t)HHt * hw;
   const size_t hbuf = (NP * hpl + 31) & ~(size_t)31;
+  constexpr int GG = (R == 4) ? 6 : 4;
+  constexpr size_t kGradBytes = UseGP<R, C>::v ? 2 * sizeof(float2) * (size_t)(kTW + GG + 2 * R - 2) * (kTH + GG + 2 * R - 2) : 0;
   const size_t smem = ((((LH ? sizeof(uint2) : sizeof(float4)) * 648 * LW) + 127) & ~(size_t)127) +
-                      sizeof(float) * (nbuf * hbuf + (size_t)NP * (kTW + 2 * R - 1) * (kTH + 2 * R - 1));
+                      sizeof(float) * (nbuf * hbuf + (((size_t)NP * (kTW + 2 * R - 1) * (kTH + 2 * R - 1) + 3) & ~(size_t)3)) + kGradBytes;
   auto kern = use_tma ? ravu_kernel<R, C, KEYMODE, NT, LH, OF32, true> : ravu_kernel<R, C, KEYMODE, NT, LH, OF32, false>;
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
