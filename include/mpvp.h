@@ -207,10 +207,23 @@ int mpvp_resample_launch_io(int device, int kernel, const void* in, void* out, i
                             int out_w, float offset_x, float offset_y, int64_t in_stride_p, int64_t in_stride_y,
                             int64_t out_stride_p, int64_t out_stride_y, const mpvp_io* io, void* stream);
 
-/* ---- host-buffer convenience (the end-to-end path: H2D + kernel + D2H inside the call) --------- */
+/* ---- host-buffer entry points (the end-to-end path: H2D + kernel(s) + D2H inside the call) ------------------------------
+ * HOST pointers (pageable or pinned) to contiguous planes [n][c][h][w] in, [n][c][out_h][out_w] out; `io` as in the *_io
+ * launches (NULL = float32).  The call stages the frames through device scratch it allocates, in chunks on two streams,
+ * and returns after the last copy has completed.  c = 1 for MPVP_KEY_LUMA, else 3. */
 int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
                         float ar_strength, const float* host_in, float* host_out, int n, int h,
                         int w);
+int mpvp_ravu_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                   const void* host_in, void* host_out, int n, int h, int w, const mpvp_io* io);
+int mpvp_ravu3x_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int key_mode,
+                     const void* host_in, void* host_out, int n, int h, int w, const mpvp_io* io);
+int mpvp_ravu_zoom_host(const mpvp_weights* lut, const mpvp_weights* lut_ar, const mpvp_key_params* key,
+                        int radius, int key_mode, float ar_strength, const void* host_in, void* host_out,
+                        int n, int h, int w, int out_h, int out_w, const mpvp_io* io);
+/* nn_y / nn_x: weights of double_y / double_x; either may be NULL (per-axis //!WHEN): [n][h][w] -> [n][2h or h][2w or w] */
+int mpvp_nnedi3_host(const mpvp_weights* nn_y, const mpvp_weights* nn_x, const void* host_in, void* host_out,
+                     int n, int h, int w, const mpvp_io* io);
 
 #ifdef __cplusplus
 }

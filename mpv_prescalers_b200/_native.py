@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # MPVP_LIB: load an experiment build (tools/build_variant.py) instead of the product library
 LIB_PATH = os.environ.get("MPVP_LIB") or os.path.join(HERE, "libmpvp.so")
-SOURCES = ["abi.cu", "ravu_lite.cu", "ravu_lite_ar.cu", "ravu_3x.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu", "resample.cu"]
+SOURCES = ["abi.cu", "ravu_lite.cu", "ravu_lite_ar.cu", "ravu_3x.cu", "ravu.cu", "ravu_zoom.cu", "nnedi3.cu", "nnedi3_tc.cu", "resample.cu", "host_entry.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -148,6 +148,10 @@ SIGNATURES = {
     "mpvp_nnedi3_launch_io": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _iop, _vp]),
     "mpvp_resample_launch_io": (_i, [_i, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i64, _i64, _i64, _i64, _iop, _vp]),
     "mpvp_ravu_lite_host": (_i, [_vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i]),
+    "mpvp_ravu_host": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _iop]),
+    "mpvp_ravu3x_host": (_i, [_vp, _kp, _i, _i, _vp, _vp, _i, _i, _i, _iop]),
+    "mpvp_ravu_zoom_host": (_i, [_vp, _vp, _kp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _i, _iop]),
+    "mpvp_nnedi3_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _iop]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

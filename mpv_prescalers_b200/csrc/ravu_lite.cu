@@ -50,49 +50,3 @@ extern "C" int mpvp_ravu_lite_launch_io(const mpvp_weights* lut, const mpvp_key_
   }
   return MPVP_E_INVALID;
 }
-
-extern "C" int mpvp_ravu_lite_host(const mpvp_weights* lut, const mpvp_key_params* key, int radius, int ar,
-                                   float ar_strength, const float* host_in, float* host_out, int n, int h, int w) {
-  MPVP_REQUIRE(lut && lut->kind == 0, "lut handle is null or not a LUT");
-  MPVP_REQUIRE(host_in && host_out, "null host pointer");
-  MPVP_REQUIRE(n >= 0 && h >= 1 && w >= 1, "bad frame geometry n=%d h=%d w=%d", n, h, w);
-  if (n == 0) return MPVP_OK;
-  DeviceGuard guard(lut->device);
-  MPVP_REQUIRE(guard.ok, "cannot switch to device %d", lut->device);
-  const size_t in_frame = (size_t)h * w, out_frame = in_frame * 4;
-  const int chunk = n < 4 ? n : 4;
-  cudaStream_t st[2] = {nullptr, nullptr};
-  float* din[2] = {nullptr, nullptr};
-  float* dout[2] = {nullptr, nullptr};
-  int rc = MPVP_OK;
-  cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&din[i], chunk * in_frame * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&dout[i], chunk * out_frame * sizeof(float));
-  }
-  for (int f0 = 0, k = 0; f0 < n && e == cudaSuccess && rc == MPVP_OK; f0 += chunk, ++k) {
-    const int b = k & 1, m = (n - f0) < chunk ? (n - f0) : chunk;
-    e = cudaMemcpyAsync(din[b], host_in + (size_t)f0 * in_frame, m * in_frame * sizeof(float), cudaMemcpyHostToDevice, st[b]);
-    if (e != cudaSuccess) break;
-    rc = mpvp_ravu_lite_launch(lut, key, radius, ar, ar_strength, din[b], dout[b], m, h, w, (int64_t)in_frame, w,
-                               (int64_t)out_frame, 2 * w, nullptr, st[b]);
-    if (rc != MPVP_OK) break;
-    e = cudaMemcpyAsync(host_out + (size_t)f0 * out_frame, dout[b], m * out_frame * sizeof(float), cudaMemcpyDeviceToHost, st[b]);
-  }
-  for (int i = 0; i < 2; ++i) {
-    if (st[i]) {
-      cudaError_t e2 = cudaStreamSynchronize(st[i]);
-      if (e == cudaSuccess) e = e2;
-      cudaStreamDestroy(st[i]);
-    }
-    if (din[i]) cudaFree(din[i]);
-    if (dout[i]) cudaFree(dout[i]);
-  }
-  if (rc != MPVP_OK) return rc;
-  if (e != cudaSuccess) {
-    set_error("mpvp_ravu_lite_host: %s", cudaGetErrorString(e));
-    return MPVP_E_CUDA;
-  }
-  return MPVP_OK;
-}

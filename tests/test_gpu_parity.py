@@ -643,6 +643,50 @@ def test_c_abi_host_entry_point():
     assert np.array_equal(out, ref)
 
 
+def test_c_abi_host_entry_points_all_families():
+    """mpvp_{ravu,ravu3x,ravu_zoom,nnedi3}_host: host planes in, host planes out, equal to prescale() on the device."""
+    import ctypes
+
+    from mpv_prescalers_b200 import HookFile, _native, prescale
+    from mpv_prescalers_b200.api import upload_weights
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    lib = _native.lib()
+
+    def run(name, fn, out_shape, extra, osz=None, u8=False):
+        hk = HookFile.parse(hook_path(name))
+        v = hk.variant
+        x = batch(5, v.channels, 44, 60, config=71)
+        W = upload_weights(hk, 0)
+        io = None
+        if u8:
+            x = np.rint(np.clip(x, 0, 1) * 255).astype(np.uint8)
+            io = _native.IoDesc(_native.FMT_U8, _native.FMT_U8, 255.0, 255.0)
+        out = np.empty((5, v.channels) + out_shape, x.dtype)
+        rc = fn(W, v, x, out, ctypes.byref(io) if io is not None else None)
+        _native.check(rc, name)
+        xt = torch.from_numpy(x).cuda()
+        ref = prescale(xt if v.channels == 3 else xt[:, 0], hk, output_size=osz)
+        ref = ref if v.channels == 3 else ref[:, None]
+        assert np.array_equal(out, ref.cpu().numpy()), f"{name}: host entry point differs from the device path"
+
+    km = {"luma": 0, "yuv": 1, "rgb": 2}
+    run("ravu-r3.hook", lambda W, v, x, o, io: lib.mpvp_ravu_host(W.handles["lut"], ctypes.byref(W.key), v.radius, km[v.plane],
+        x.ctypes.data, o.ctypes.data, 5, 44, 60, io), (88, 120), None)
+    run("ravu-r2-rgb.hook", lambda W, v, x, o, io: lib.mpvp_ravu_host(W.handles["lut"], ctypes.byref(W.key), v.radius, km[v.plane],
+        x.ctypes.data, o.ctypes.data, 5, 44, 60, io), (88, 120), None, u8=True)
+    run("compute/ravu-3x-r2.hook", lambda W, v, x, o, io: lib.mpvp_ravu3x_host(W.handles["lut"], ctypes.byref(W.key), v.radius,
+        km[v.plane], x.ctypes.data, o.ctypes.data, 5, 44, 60, io), (132, 180), None)
+    run("ravu-zoom-r2.hook", lambda W, v, x, o, io: lib.mpvp_ravu_zoom_host(W.handles["lut"], W.handles.get("lut_ar"),
+        ctypes.byref(W.key), v.radius, km[v.plane], float(v.ar_strength), x.ctypes.data, o.ctypes.data, 5, 44, 60, 101, 150, io),
+        (101, 150), None, osz=(101, 150))
+    run("nnedi3-nns32-win8x4.hook", lambda W, v, x, o, io: lib.mpvp_nnedi3_host(W.handles["y"], W.handles["x"], x.ctypes.data,
+        o.ctypes.data, 5, 44, 60, io), (88, 120), None)
+    run("nnedi3-nns16-win8x6.hook", lambda W, v, x, o, io: lib.mpvp_nnedi3_host(W.handles["y"], None, x.ctypes.data,
+        o.ctypes.data, 5, 44, 60, io), (88, 60), None, osz=(88, 70))
+
+
 def test_c_abi_error_convention():
     import ctypes
 
