@@ -396,6 +396,7 @@ def prescale(
     out_bit_depth: Optional[int] = None,
     split: str = "frames",
     correct_offset: Union[bool, str] = False,
+    runner: str = "fused",
 ):
     """Apply one mpv-prescalers hook file to a batch of frames.
 
@@ -426,11 +427,26 @@ def prescale(
                   same size, shifted by the accumulated offset) so that the result is aligned like ravu-lite's and
                   ``.offset`` is (0, 0); hooks without an offset are returned as they are.
 
+    runner        'fused' (default): the hand-written kernels, which accept the shipped files and refuse anything else
+                  (``HookError``); 'generic': transpile the file's GLSL to CUDA at load time (NVRTC) and run it pass by
+                  pass (``hookrunner.GenericHook``: any fragment-shader hook within the GLSL subset, e.g. a hand-modified
+                  RAVU; float32 planes only, slow); 'auto': fused if the file is a known form, else generic.
+
     Returns the output tensor (same rank as the input) carrying ``.offset`` (accumulated ``//!OFFSET``,
     (x, y) in output pixels), ``.applied`` and ``.plan``; with ``return_buckets=True`` a pair
     ``(out, buckets)`` where ``buckets`` holds the LUT row of every key evaluation (RAVU families).
     """
     hk = hook if isinstance(hook, HookFile) else HookFile.parse(find_hook(hook))
+    if runner not in ("fused", "generic", "auto"):
+        raise ValueError("runner must be 'fused', 'generic' or 'auto'")
+    if runner == "auto":
+        try:
+            hk.variant
+            runner = "fused"
+        except HookError:
+            runner = "generic"
+    if runner == "generic":
+        return _prescale_generic(frames, hk, output_size, lut_precision, is_yuv, correct_offset)
     v = hk.variant
     scaler = None
     if correct_offset:
@@ -513,6 +529,35 @@ def prescale(
     res = _restore_shape(res, in_shape, c)
     res.offset, res.applied, res.plan = pl.offset, True, pl
     return (res, bk) if return_buckets else res
+
+
+def _prescale_generic(frames: torch.Tensor, hk: HookFile, output_size, lut_precision: str, is_yuv: bool, correct_offset):
+    """runner='generic': the file's own GLSL, transpiled and compiled at load time (hookrunner.py)."""
+    from .hookrunner import GenericHook
+
+    if not torch.cuda.is_available():
+        raise _native.NativeError("prescale() needs a CUDA device: there is no CPU fallback")
+    if frames.dtype != torch.float32:
+        raise TypeError("runner='generic' takes float32 planes")
+    gh = getattr(hk, "_generic_runner", None)
+    if gh is None or gh.lut_precision != lut_precision:
+        gh = hk._generic_runner = GenericHook(hk, lut_precision)
+    host = frames.device.type != "cuda"
+    x = frames.cuda() if host else frames
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x[None]
+    res, off = gh.run(x, output_size, is_yuv)
+    applied = tuple(res.shape) != tuple(x.shape) or off != (0.0, 0.0) or not torch.equal(res, x)
+    if correct_offset and off != (0.0, 0.0):
+        res = resample(res, None, off, "lanczos" if correct_offset is True else str(correct_offset))
+        off = (0.0, 0.0)
+    if squeeze:
+        res = res[0]
+    if host:
+        res = res.cpu()
+    res.offset, res.applied, res.plan = off, applied, None
+    return res
 
 
 def resample(frames: torch.Tensor, output_size: Optional[Tuple[int, int]] = None, offset: Tuple[float, float] = (0.0, 0.0),

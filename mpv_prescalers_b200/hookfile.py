@@ -641,8 +641,31 @@ def _nnedi3_pass(p: Pass, nns: int, win: Tuple[int, int], direction: str, where:
     return Nnedi3Weights(w1.reshape(nns, 8, S), w2.reshape(nns, 8, S), b1, b2)
 
 
+_AR_MIX_RE = re.compile(r"(mix\(res, clamp\(res, lo, hi\), )" + _FLT + r"\)")
+
+
+def body_signature(body: str) -> str:
+    """Identity of a pass body for the shipped-form check: sha256 of its text with the one documented tunable (the
+    anti-ringing strength literal, README.md:64) masked."""
+    return hashlib.sha256(_AR_MIX_RE.sub(r"\1S)", body).encode()).hexdigest()[:20]
+
+
 def classify(hook: HookFile) -> Variant:
     """Work out which prescaler a parsed file is and extract everything the kernels need."""
+    from .known_bodies import KNOWN_BODIES
+
+    v = _classify(hook)   # structural checks first: they name what differs (Gaussian weights, stencils, LUT geometry ...)
+    # The fused kernels implement the shipped shaders.  A file whose GLSL differs from every shipped pass body (a hand
+    # edit the structural checks did not catch) must not be run as if it were the original: it is refused here
+    # (prescale(..., runner='generic') runs the file's own GLSL instead).
+    for p in hook.passes:
+        if body_signature(p.body) not in KNOWN_BODIES:
+            raise HookError(f"{hook.path}:{p.line}: pass {p.desc!r} differs from the supported form (its GLSL is not the text of "
+                            "a shipped mpv-prescalers pass); the fused kernels refuse it -- use prescale(..., runner='generic')")
+    return v
+
+
+def _classify(hook: HookFile) -> Variant:
     first = hook.passes[0]
     fam = None
     for name, pat in _DESC_PATTERNS:
