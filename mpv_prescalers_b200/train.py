@@ -1,0 +1,134 @@
+"""LUT trainer for the RAVU-Lite family: the piece of the absent upstream ``source`` branch
+(``README.md:3-4``) that produces a ``//!TEXTURE`` weight LUT from example images.
+
+RAVU is "rapid and accurate" learned upscaling: the 2x2 output pixels of every source pixel are a linear filter of the
+source window, with one filter per (angle, strength, coherence) bucket of the window's structure tensor
+(``ravu-lite-r3.hook:15-120``).  Training = one least-squares problem per bucket: minimise, over all source pixels of the
+training planes that fall into the bucket, the squared error between the filtered window and the true high-resolution
+pixels.  The shipped LUTs are point-symmetric -- tap ``N-1-t`` of phase ``c`` carries the weight of tap ``t`` of phase
+``3-c``, which is what lets the shader store half the taps and fetch ``w.wzyx`` for the mirrored one
+(``ravu-lite-r3.hook:97-118``; verified on the shipped payloads: centre texel ``.x == .w``, ``.y == .z`` exactly) -- so
+each bucket is solved for two weight vectors ``W_0, W_1`` on the data augmented with its 180-degree rotation, and
+``W_3 = reverse(W_0)``, ``W_2 = reverse(W_1)``.
+
+Everything runs on the GPU: the buckets come from the same CUDA key kernel the hook uses at run time
+(``prescale(..., return_buckets=True)``), the normal equations are accumulated per bucket in float64, and the result is
+written back as a complete ``.hook`` file (the original GLSL, a new payload line), which ``prescale()`` accepts like a
+shipped file.  The reference's own training set and hyper-parameters are not in the snapshot, so a LUT trained here is a
+NEW filter, not a reconstruction of the shipped one; the self-consistency test trains on planes upscaled by a shipped LUT
+and recovers that LUT.  The anti-ringing LUT of ravu-zoom (``ravu_zoom_lut3_ar``, ``.MISSING_LARGE_BLOBS``) has no
+training objective stated anywhere in the reference and is not covered.
+"""
+from __future__ import annotations
+
+import re
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .hookfile import HookError, HookFile
+
+__all__ = ["train_ravu_lite", "write_hook_with_lut", "lut_to_hex"]
+
+
+def _windows(lr: torch.Tensor, radius: int) -> torch.Tensor:
+    """[H, W] -> [H*W, N] source windows in the shader's tap order t = i*n + j (i <-> dx, j <-> dy), clamp-to-edge."""
+    n, o = 2 * radius - 1, radius - 1
+    h, w = lr.shape
+    p = torch.nn.functional.pad(lr[None, None], (o, o, o, o), mode="replicate")[0, 0]
+    cols = []
+    for i in range(n):          # dx = i - o
+        for j in range(n):      # dy = j - o
+            cols.append(p[j:j + h, i:i + w].reshape(-1))
+    return torch.stack(cols, dim=1)
+
+
+def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: float = 1e-9, min_samples: Optional[int] = None,
+                    exclude_clipped: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Least-squares LUT of a RAVU-Lite hook from training pairs.
+
+    hook   a ``ravu-lite(-ar)-rN.hook``: its key constants decide the buckets, its LUT fills buckets that see too few samples;
+    lr     ``[F, H, W]`` float32 CUDA planes in [0, 1];  hr  ``[F, 2H, 2W]``: the true 2x planes, centre-aligned like the
+           shader's output (phase c of source pixel (x, y) is hr[2y + c % 2, 2x + c // 2], ``ravu-lite-r3.hook:128-134``);
+    ridge  Tikhonov term relative to the mean diagonal of the normal matrix;
+    exclude_clipped  drop source pixels with a target at exactly 0 or 1 (the shader clamps its result to [0, 1], which
+           makes such pixels uninformative about the linear filter).
+
+    Returns ``(lut [288, LW, 4] float32, samples_per_bucket [288])``."""
+    from .api import prescale
+
+    v = hook.variant
+    if v.family != "ravu-lite":
+        raise HookError("train_ravu_lite() trains the RAVU-Lite family")
+    if lr.device.type != "cuda" or hr.device.type != "cuda":
+        raise ValueError("training planes must be CUDA tensors")
+    f, h, w = lr.shape
+    if tuple(hr.shape) != (f, 2 * h, 2 * w):
+        raise ValueError(f"hr must be {(f, 2 * h, 2 * w)}, got {tuple(hr.shape)}")
+    r = v.radius
+    n = 2 * r - 1
+    N, half = n * n, (n * n - 1) // 2
+    rows = 288
+    dev = lr.device
+    A = torch.zeros((rows, N, N), dtype=torch.float64, device=dev)
+    B = torch.zeros((rows, N, 2), dtype=torch.float64, device=dev)
+    count = torch.zeros(rows, dtype=torch.int64, device=dev)
+    rev = torch.arange(N - 1, -1, -1, device=dev)
+    _, buckets = prescale(lr, hook, return_buckets=True)       # the hook's own key kernel
+    for k in range(f):
+        X = _windows(lr[k], r)                                   # [P, N]
+        H = hr[k]
+        Y = torch.stack([H[0::2, 0::2], H[1::2, 0::2], H[0::2, 1::2], H[1::2, 1::2]], dim=-1).reshape(-1, 4)   # phases 0..3
+        b = buckets[k].reshape(-1).long()
+        if exclude_clipped:
+            keep = ((Y > 0.0) & (Y < 1.0)).all(dim=1)
+            X, Y, b = X[keep], Y[keep], b[keep]
+        order = torch.argsort(b)
+        X, Y, b = X[order], Y[order], b[order]
+        cnt = torch.bincount(b, minlength=rows)
+        count += cnt
+        starts = torch.cumsum(cnt, 0) - cnt
+        for row in torch.nonzero(cnt).reshape(-1).tolist():
+            s, m = int(starts[row]), int(cnt[row])
+            xb = X[s:s + m].double()
+            yb = Y[s:s + m].double()
+            xr = xb[:, rev]                                      # the window rotated by 180 degrees
+            A[row] += xb.T @ xb + xr.T @ xr
+            # W_0 sees (x, y_0) and (rev x, y_3); W_1 sees (x, y_1) and (rev x, y_2)
+            B[row, :, 0] += xb.T @ yb[:, 0] + xr.T @ yb[:, 3]
+            B[row, :, 1] += xb.T @ yb[:, 1] + xr.T @ yb[:, 2]
+    lut_old = np.asarray(v.lut.data, dtype=np.float32)           # [288, LW, 4]
+    lut = lut_old.copy()
+    need = (4 * N) if min_samples is None else int(min_samples)
+    count_h = count.cpu().numpy()
+    eye = torch.eye(N, dtype=torch.float64, device=dev)
+    for row in range(rows):
+        if count_h[row] < need:
+            continue                                             # too few samples: the hook's own row stays
+        a = A[row]
+        lam = ridge * float(torch.diagonal(a).mean())
+        Wsol = torch.linalg.solve(a + lam * eye, B[row]).cpu().numpy()   # [N, 2] = (W_0, W_1)
+        W0, W1 = Wsol[:, 0], Wsol[:, 1]
+        for t in range(half + 1):
+            lut[row, t] = (W0[t], W1[t], W1[N - 1 - t], W0[N - 1 - t])
+    return lut.astype(np.float32), count_h
+
+
+def lut_to_hex(lut: np.ndarray) -> str:
+    """``[h, w, 4]`` float32 -> the payload line of a ``//!TEXTURE`` block (little-endian float32, lowercase hex)."""
+    return np.ascontiguousarray(lut, dtype="<f4").tobytes().hex()
+
+
+def write_hook_with_lut(hook: HookFile, lut: np.ndarray, path: str) -> None:
+    """Write a complete hook file: the text of ``hook`` with the payload of its (single) LUT replaced by ``lut``."""
+    v = hook.variant
+    if lut.shape != (v.lut.height, v.lut.width, 4):
+        raise ValueError(f"LUT must be {(v.lut.height, v.lut.width, 4)}, got {lut.shape}")
+    with open(hook.path) as f:
+        text = f.read()
+    pat = re.compile(r"(//!TEXTURE " + re.escape(v.lut.name) + r"\n(?://![^\n]*\n)+)([0-9a-f]+)")
+    if len(pat.findall(text)) != 1:
+        raise HookError(f"{hook.path}: cannot locate the payload of {v.lut.name}")
+    with open(path, "w") as f:
+        f.write(pat.sub(lambda m: m.group(1) + lut_to_hex(lut), text))

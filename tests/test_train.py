@@ -1,0 +1,58 @@
+"""LUT trainer: host logic on the CPU, self-consistency on the GPU."""
+import numpy as np
+import pytest
+
+from tests.conftest import hook_path
+
+
+def test_lut_hex_round_trip_and_hook_rewrite(tmp_path):
+    """A rewritten hook file keeps the GLSL byte for byte (so the fused kernels accept it) and carries the new payload."""
+    pytest.importorskip("torch")
+    from mpv_prescalers_b200 import HookFile
+    from mpv_prescalers_b200.train import lut_to_hex, write_hook_with_lut
+
+    hk = HookFile.parse(hook_path("ravu-lite-r2.hook"))
+    lut = np.asarray(hk.variant.lut.data, np.float32)
+    assert lut_to_hex(lut) in open(hk.path).read()          # the shipped payload is reproduced bit for bit
+    new = (lut * np.float32(0.5)).astype(np.float32)
+    out = tmp_path / "half.hook"
+    write_hook_with_lut(hk, new, str(out))
+    hk2 = HookFile.parse(str(out))
+    assert np.array_equal(hk2.variant.lut.data, new)
+    assert [p.body for p in hk2.passes] == [p.body for p in hk.passes]
+    assert hk2.content_key != hk.content_key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ravu-lite-r3.hook", "ravu-lite-r2.hook"])
+def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
+    """Self-consistency: high-resolution targets produced by a shipped LUT are a per-bucket LINEAR function of the source
+    windows, so least squares must give that LUT back (well-populated buckets), and the retrained hook file must
+    reproduce the original's output on a plane it has not seen."""
+    import torch
+
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from mpv_prescalers_b200.train import train_ravu_lite, write_hook_with_lut
+    from tests.parity import psnr
+
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device")
+    hk = HookFile.parse(hook_path(name))
+    rng = np.random.default_rng(5)
+    x = batch(6, 1, 360, 480, config=91)[:, 0]
+    x = np.clip(0.2 + 0.6 * x + rng.normal(0, 0.04, x.shape), 0.02, 0.98).astype(np.float32)   # full-rank windows, few clipped targets
+    lr = torch.from_numpy(x).cuda()
+    hr = prescale(lr, hk)
+    lut, count = train_ravu_lite(hk, lr, hr)
+    ref = np.asarray(hk.variant.lut.data, np.float32).astype(np.float16).astype(np.float32)      # what the kernels apply
+    well = count >= 5000
+    assert well.sum() >= 20, f"only {well.sum()} well-populated buckets"
+    assert np.abs(lut[well] - ref[well]).max() <= 2e-3, f"recovered LUT differs by {np.abs(lut[well] - ref[well]).max():.2e}"
+    starved = count < 4 * (2 * hk.variant.radius - 1) ** 2          # buckets that saw too few windows keep the hook's own row
+    assert np.array_equal(lut[starved], np.asarray(hk.variant.lut.data, np.float32)[starved])
+    out = tmp_path / "retrained.hook"
+    write_hook_with_lut(hk, lut, str(out))
+    fresh = torch.from_numpy(np.clip(0.2 + 0.6 * batch(1, 1, 200, 300, config=92)[:, 0], 0, 1).astype(np.float32)).cuda()
+    a, b = prescale(fresh, hk), prescale(fresh, str(out))
+    assert psnr(a.cpu().numpy(), b.cpu().numpy()) >= 60.0

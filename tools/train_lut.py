@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Train a RAVU-Lite LUT on the GPU and write it as a complete hook file.
+
+    python tools/train_lut.py --hook ravu-lite-r3.hook --hr planes.npy --out my-ravu-lite-r3.hook
+
+``planes.npy``: float32 [F, 2H, 2W] high-resolution luma planes in [0, 1]; the low-resolution training input is their
+2x2 box average (the usual RAVU training degradation).  Without --hr a synthetic set is used (a smoke run: the result
+is a valid filter for synthetic statistics, not a replacement of the shipped weights).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpv_prescalers_b200 import HookFile, find_hook, prescale  # noqa: E402
+from mpv_prescalers_b200.synth import batch  # noqa: E402
+from mpv_prescalers_b200.train import train_ravu_lite, write_hook_with_lut  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--hook", default="ravu-lite-r3.hook")
+    ap.add_argument("--hr", default=None, help=".npy with float32 [F, 2H, 2W] planes")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--ridge", type=float, default=1e-6)
+    args = ap.parse_args()
+    hk = HookFile.parse(find_hook(args.hook))
+    hr = np.load(args.hr).astype(np.float32) if args.hr else batch(8, 1, 720, 960, config=7)[:, 0]
+    hr = torch.from_numpy(np.ascontiguousarray(hr[:, : hr.shape[1] // 2 * 2, : hr.shape[2] // 2 * 2])).cuda()
+    lr = (hr[:, 0::2, 0::2] + hr[:, 1::2, 0::2] + hr[:, 0::2, 1::2] + hr[:, 1::2, 1::2]) * 0.25
+    before = float(((prescale(lr, hk) - hr) ** 2).mean())
+    lut, count = train_ravu_lite(hk, lr, hr, ridge=args.ridge, exclude_clipped=False)
+    write_hook_with_lut(hk, lut, args.out)
+    after = float(((prescale(lr, args.out) - hr) ** 2).mean())
+    print(f"{args.out}: {int((count >= 4 * lut.shape[1] * 2).sum())} of 288 buckets retrained on {int(count.sum())} windows; "
+          f"training MSE {before:.3e} -> {after:.3e}")
+
+
+if __name__ == "__main__":
+    main()
