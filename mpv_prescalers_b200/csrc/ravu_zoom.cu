@@ -44,7 +44,8 @@ namespace {
 struct ClassPair {
   int xsoff, ysoff;            // first x / y member segment of the two classes in the plan's segment arrays
   int tiles_x, tiles_y;        // member tiles per frame = segments of the x class  x  segments of the y class
-  int tile_start;              // first work item of this class pair (work items are class-pair major)
+  int tile_start;              // first work item of this class pair PER FRAME (work items are class-pair major; the
+                               // class pair's items of an n-frame batch start at tile_start * n)
   int pad;
 };
 
@@ -587,9 +588,9 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3)
   int cur_cp = -1;
   int cpi = 0;
   for (long long item = w_begin; item < w_end; ++item) {
-    while (cpi + 1 < A.ncp && item >= (long long)A.cps[cpi + 1].tile_start) ++cpi;
+    while (cpi + 1 < A.ncp && item >= (long long)A.cps[cpi + 1].tile_start * A.n) ++cpi;
     const ClassPair cp = A.cps[cpi];
-    const int local = (int)(item - cp.tile_start);
+    const int local = (int)(item - (long long)cp.tile_start * A.n);
     const int per_frame = cp.tiles_x * cp.tiles_y;
     const int f = local / per_frame;
     const int tl = local - f * per_frame;
@@ -894,9 +895,19 @@ struct ZoomPlan {
   std::vector<ClassPair> cps_host;
   int *xo = nullptr, *xb = nullptr, *yo = nullptr, *yb = nullptr;
   int2 *xseg = nullptr, *yseg = nullptr;
+  ClassPair* cps = nullptr;
   float* plut = nullptr;
+  // key-map scratch of the pre-pass, owned by the plan and grown on demand: launches allocate nothing in the steady
+  // state (a stream-ordered cudaMallocAsync would be re-allocated after every synchronisation of the caller: the
+  // default pool trims to zero).  `kmap_ev` orders a launch after the previous user of the buffer, whatever its stream.
+  std::mutex kmu;
+  unsigned short* kmap = nullptr;
+  size_t kmap_cap = 0;
+  cudaEvent_t kmap_ev = nullptr;
   ~ZoomPlan() {
-    cudaFree(xo); cudaFree(xb); cudaFree(yo); cudaFree(yb); cudaFree(xseg); cudaFree(yseg); cudaFree(plut);
+    cudaFree(xo); cudaFree(xb); cudaFree(yo); cudaFree(yb); cudaFree(xseg); cudaFree(yseg); cudaFree(cps); cudaFree(plut);
+    if (kmap_ev) { cudaEventSynchronize(kmap_ev); cudaEventDestroy(kmap_ev); }
+    cudaFree(kmap);
   }
 };
 struct ZoomPlanCache {
@@ -970,6 +981,7 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
   if (e == cudaSuccess) e = upload(z->yb, ay.b);
   if (e == cudaSuccess) e = upload(z->xseg, ax.seg);
   if (e == cudaSuccess) e = upload(z->yseg, ay.seg);
+  if (e == cudaSuccess) e = upload(z->cps, z->cps_host);
   if (e == cudaSuccess) e = upload(rep_x, ax.rep);
   if (e == cudaSuccess) e = upload(rep_y, ay.rep);
   if (e == cudaSuccess) e = cudaMalloc(&z->plut, sizeof(float) * (size_t)z->ncp * 288 * PL);
@@ -995,28 +1007,26 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
 template <int R, int C, int KEYMODE, bool AR>
 int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) {
   // work items are class-pair major and cover all frames of a class pair before the next one starts
-  std::vector<ClassPair> cps(z->cps_host);
-  long long total = 0;
-  for (ClassPair& cp : cps) {
-    MPVP_REQUIRE(total < (1LL << 30), "batch too large for the phase path");
-    cp.tile_start = (int)total;
-    total += (long long)cp.tiles_x * cp.tiles_y * a.n;
-  }
+  const long long total = (long long)z->total_tiles_per_frame * a.n;
   MPVP_REQUIRE(total < (1LL << 31), "batch too large: %lld tiles (limit 2^31)", total);
-  // the class-pair table depends on n: tiny stream-ordered upload (cudaMemcpyAsync from pageable memory stages the source
-  // before it returns, so the local vector may die right after)
-  ClassPair* d_cps = nullptr;
-  MPVP_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_cps), sizeof(ClassPair) * cps.size(), stream));
-  cudaError_t e = cudaMemcpyAsync(d_cps, cps.data(), sizeof(ClassPair) * cps.size(), cudaMemcpyHostToDevice, stream);
-  unsigned short* kmap = nullptr;
   const size_t kbytes = sizeof(unsigned short) * (size_t)a.n * (a.h + 1) * (a.w + 1);
-  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&kmap), kbytes, stream);
-  if (e != cudaSuccess) {
-    cudaFreeAsync(d_cps, stream);
-    MPVP_CUDA_OK(e);
+  std::lock_guard<std::mutex> klk(z->kmu);
+  if (!z->kmap_ev) MPVP_CUDA_OK(cudaEventCreateWithFlags(&z->kmap_ev, cudaEventDisableTiming));
+  if (z->kmap_cap < kbytes) {   // first use of this geometry, or a larger batch than before
+    if (z->kmap) {
+      MPVP_CUDA_OK(cudaEventSynchronize(z->kmap_ev));
+      cudaFree(z->kmap);
+      z->kmap = nullptr;
+      z->kmap_cap = 0;
+    }
+    MPVP_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&z->kmap), kbytes));
+    z->kmap_cap = kbytes;
+  } else {
+    MPVP_CUDA_OK(cudaStreamWaitEvent(stream, z->kmap_ev, 0));   // the previous launch that used the buffer (any stream)
   }
-  a.kmap = kmap;
-  a.xo = z->xo; a.xb = z->xb; a.yo = z->yo; a.yb = z->yb; a.xseg = z->xseg; a.yseg = z->yseg; a.cps = d_cps; a.ncp = z->ncp; a.plut = z->plut;
+  cudaError_t e = cudaSuccess;
+  a.kmap = z->kmap;
+  a.xo = z->xo; a.xb = z->xb; a.yo = z->yo; a.yb = z->yb; a.xseg = z->xseg; a.yseg = z->yseg; a.cps = z->cps; a.ncp = z->ncp; a.plut = z->plut;
   a.sw = z->sw; a.sh = z->sh;
   int rc = MPVP_OK;
   {
@@ -1085,8 +1095,7 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
     }
   }
   e = cudaGetLastError();
-  cudaFreeAsync(kmap, stream);
-  cudaFreeAsync(d_cps, stream);
+  if (e == cudaSuccess) e = cudaEventRecord(z->kmap_ev, stream);
   if (rc != MPVP_OK) return rc;
   MPVP_CUDA_OK(e);
   return MPVP_OK;
@@ -1094,8 +1103,12 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
 
 template <int R, int C, int KEYMODE, bool AR>
 int launch_zoom(const ZoomArgs& a, const mpvp_weights* lut, const mpvp_weights* lut_ar, int device, cudaStream_t stream, bool half_lut) {
-  // MPVP_ZOOM_PHASE=0 forces the general per-pixel path (A/B switch and cross-check)
-  if (env_flag("MPVP_ZOOM_PHASE", true) && !env_flag("MPVP_ZOOM_TEX", false)) {
+  // MPVP_ZOOM_PHASE=0 forces the general per-pixel path (A/B switch and cross-check).  Three-channel planes take the
+  // general path by default (MPVP_ZOOM_PHASE=3 forces the phase path): without the shared register window of the luma
+  // strips the phase kernel is slower there (zoom-r2-yuv 720p->2160p x4: 1.02 vs 0.82 ms).
+  const char* pe = getenv("MPVP_ZOOM_PHASE");
+  const bool phase_ok = C == 1 ? env_flag("MPVP_ZOOM_PHASE", true) : (pe && pe[0] == '3');
+  if (phase_ok && !env_flag("MPVP_ZOOM_TEX", false)) {
     if (ZoomPlan* z = get_plan<R, AR>(lut, lut_ar, a.h, a.w, a.oh, a.ow, C, stream))
       return launch_zoom_phase<R, C, KEYMODE, AR>(a, z, device, stream);
   }
