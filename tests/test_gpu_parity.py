@@ -149,6 +149,35 @@ def test_ravu_zoom_matches_oracle(name, in_hw, out_hw):
     _run_ravu_variant(name, n=2, h=in_hw[0], w=in_hw[1], config=13, out_hw=out_hw)
 
 
+@pytest.mark.parametrize("name,in_hw,out_hw", [
+    ("ravu-zoom-r3.hook", (120, 200), (360, 600)),        # 3x: knife-edge classes
+    ("ravu-zoom-r2.hook", (120, 200), (240, 400)),        # 2x: phases on LUT nodes
+    ("ravu-zoom-r3.hook", (120, 200), (180, 300)),        # 3/2
+    ("ravu-zoom-r2.hook", (90, 150), (120, 200)),         # 4/3: neighbouring class members three texels apart
+    ("ravu-zoom-r3.hook", (97, 131), (211, 307)),         # no small phase set: both settings take the general path
+    ("ravu-zoom-r2-rgb.hook", (60, 100), (180, 300)),     # three channels (phase path on request only)
+    ("ravu-zoom-ar-r2.hook", (1280 // 8, 1280 // 4), (3 * 1280 // 8, 3 * 1280 // 4)),   # -AR: phase path only for single-valued node classes
+])
+def test_zoom_phase_path_agrees_with_general_path(name, in_hw, out_hw, monkeypatch):
+    """The phase path (key pre-pass + per-class phase LUT) against the per-pixel general path, which is bit-faithful to
+    the oracle's sampler arithmetic: identical buckets, outputs within 5e-4 (the phase LUT is built at a class's
+    representative sub-pixel phase, members differ from it by fp32 noise of `pos`; its outer taps are binary16)."""
+    from mpv_prescalers_b200 import HookFile, prescale
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    x = torch.from_numpy(_frames(hk.variant, 2, in_hw[0], in_hw[1], 45)).cuda()
+    if hk.variant.channels == 1:
+        x = x[:, 0]
+    monkeypatch.setenv("MPVP_ZOOM_PHASE", "0")
+    ref, bref = prescale(x, hk, output_size=out_hw, return_buckets=True)
+    monkeypatch.setenv("MPVP_ZOOM_PHASE", "3")
+    got, bgot = prescale(x, hk, output_size=out_hw, return_buckets=True)
+    torch.cuda.synchronize()
+    assert torch.equal(bref, bgot)
+    assert float((ref - got).abs().max()) <= 5e-4, f"{name} {in_hw}->{out_hw}: {float((ref - got).abs().max()):.3e}"
+
+
 def test_config1_ravu_lite_r3_960x540():
     """BASELINE.json configs[0]: ravu-lite-r3 2x luma upscale of one synthetic 960x540 plane."""
     stats = _run_ravu_variant("ravu-lite-r3.hook", n=1, h=540, w=960, config=1)
