@@ -168,7 +168,23 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   constexpr int KX = K + 16;                // + one MMA K-step carrying the biases
   constexpr int KC = K / 8;                 // 16-byte K chunks written per tile
   constexpr int N = 2 * NNS;                // accumulator columns per pixel
-  constexpr int CN = N < 128 ? N : 128;     // columns per MMA chunk (64 neurons)
+  // PP (ping-pong, networks with >= 128 accumulator columns): the warpgroup's 128 TMEM columns are two 64-column slots; a
+  // chunk's 64 columns are loaded into registers at the top of the chunk, which frees its slot for the MMA after next, and
+  // the MMA of the NEXT chunk is issued at the same point into the other slot -- so no warp ever waits in a warpgroup
+  // barrier inside a tile, and the warps of a warpgroup (which sit on four different SM sub-partitions) may drift by up to
+  // a chunk.  Stall sampling of the barrier-synchronised schedule: 17 % of all warp samples sit in the chunk-boundary
+  // barrier, the wait for the MMA it releases, and the tile-start wait (profiles/r02 notes in DESIGN.md 4.5).
+  // MEASURED SLOWER and compiled out: nns256-win8x6 6.01 vs 4.67 ms, nns128-win8x4 3.01 vs 2.51, nns64-win8x6 2.01 vs 1.75.
+  // An SS-mode tcgen05.mma re-reads its A operand from shared memory for every instruction: per K = 16 step 4 KB of A
+  // + N * 32 B of B.  At N = 64 that is 6 KB per 32 tensor cycles = 192 B/clk against the 128 B/clk of an SM's shared
+  // memory; at N = 128 (the barrier-synchronised schedule) 8 KB per 64 cycles = exactly 128 B/clk.  Small-N MMAs are
+  // shared-memory bound and starve the LDS / STS of the other warpgroups; a ping-pong schedule needs the A operand in
+  // tensor memory (tcgen05.mma with A from TMEM), for which 4 x (128 accumulator + 32 A) columns do not fit in 512.
+#ifndef MPVP_X_NN_PP
+#define MPVP_X_NN_PP 0
+#endif
+  constexpr bool PP = MPVP_X_NN_PP && N >= 128 && EPI == 3;
+  constexpr int CN = PP ? 64 : (N < 128 ? N : 128);     // columns per MMA chunk
   constexpr int NCH = N / CN;
   // Small networks (nns16 / nns32: one chunk of <= 64 columns per tile) keep TWO tiles in flight per warpgroup: the A
   // operand and the MMA of tile t+1 are issued before the epilogue of tile t starts (two A buffers, two TMEM slots,
@@ -196,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   unsigned char* s_b = smem;                               // B operand
   unsigned char* s_a = s_b + kBBytes;                      // A operand, one per warpgroup
   float* s_stage = reinterpret_cast<float*>(s_a + kWG * NA * kABytes);  // [kWG][STG]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] MMA done, + 1 (B operand), + [kWG] staging
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 3 * kWG + 1);
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_stage + kWG * STG);  // [kWG][2] MMA done, + 1 (B operand), + [kWG] staging, + [kWG][2] slot free (PP)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 5 * kWG + 1);
 
   const int tid = threadIdx.x;
   const int wg = tid >> 7;       // warpgroup
@@ -210,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     for (int i = 0; i < 2 * kWG; ++i) mbar_init(smem_u32(s_mbar + i), 1);
     mbar_init(mbar_b, 1);
     for (int i = 0; i < kWG; ++i) mbar_init(smem_u32(s_mbar + 2 * kWG + 1 + i), 1);
+    for (int i = 0; i < 2 * kWG; ++i) mbar_init(smem_u32(s_mbar + 3 * kWG + 1 + i), 4);   // one arrival per warp
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
@@ -244,6 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
   const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
+  const uint32_t free_bar = smem_u32(s_mbar + 3 * kWG + 1 + 2 * wg);   // PP: [2] "slot loaded into registers by all four warps"
+  uint32_t full_par = 0, free_par = 0;                                  // PP: parity bits of the two full / free barriers
   const uint32_t stage_bar = smem_u32(s_mbar + 2 * kWG + 1 + wg);
   uint32_t stage_phase = 0;   // parity of this warpgroup's staging barrier (TMA)
   const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
@@ -403,6 +422,63 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
     // ---- epilogue -----------------------------------------------------------------------------
     float wsum = 0.f, vsum = 0.f;
     float2 wsum2 = make_float2(0.f, 0.f), vsum2 = make_float2(0.f, 0.f);
+    if constexpr (PP) {
+      // 16 neurons: registers 0..15 softmax logits, 16..31 their elliott inputs; one Newton reciprocal per 8 neurons
+      auto math32 = [&](const uint32_t (&cur)[32]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float2 s1[4], u[4], pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i0 = 8 * g + 2 * k;
+            s1[k].x = ex2_approx(__uint_as_float(cur[i0]));
+            s1[k].y = ex2_approx(__uint_as_float(cur[i0 + 1]));
+            const float2 t = make_float2(__uint_as_float(cur[16 + i0]), __uint_as_float(cur[16 + i0 + 1]));
+            u[k].x = 1.0f + fabsf(t.x);
+            u[k].y = 1.0f + fabsf(t.y);
+            pk[k] = __fmul2_rn(s1[k], t);
+          }
+          const float2 n01 = __ffma2_rn(pk[1], u[0], __fmul2_rn(pk[0], u[1]));
+          const float2 n23 = __ffma2_rn(pk[3], u[2], __fmul2_rn(pk[2], u[3]));
+          const float2 d01 = __fmul2_rn(u[0], u[1]), d23 = __fmul2_rn(u[2], u[3]);
+          const float2 num = __ffma2_rn(n23, d01, __fmul2_rn(n01, d23));
+          const float2 den = __fmul2_rn(d01, d23);
+          float2 rn;
+          rn.x = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(den.x));
+          rn.y = __int_as_float((int)(0x7EF311C7u + 0x80000000u) - __float_as_int(den.y));
+          rn = __fmul2_rn(rn, __ffma2_rn(den, rn, make_float2(2.f, 2.f)));
+          rn = __fmul2_rn(rn, __ffma2_rn(den, rn, make_float2(2.f, 2.f)));
+          vsum2 = __ffma2_rn(num, rn, vsum2);   // accumulates -vsum
+          wsum2 = __fadd2_rn(wsum2, __fadd2_rn(__fadd2_rn(s1[0], s1[1]), __fadd2_rn(s1[2], s1[3])));
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t sl = (uint32_t)(c & 1);
+        mbar_wait(my_mbar + 8u * sl, (full_par >> sl) & 1u);
+        full_par ^= 1u << sl;
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld32_issue(d_lane + sl * 64u, va);
+        tmem_ld32_issue(d_lane + sl * 64u + 32u, vb);
+        tmem_ld_wait();
+        // this warp's share of the slot is in registers
+        tc_fence_before();
+        if (c + 2 < NCH && (lt & 31) == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(free_bar + 8u * sl) : "memory");
+        if (lt == 0 && c + 1 < NCH) {
+          // MMA of the next chunk into the other slot: every warp loaded that slot's previous contents a chunk ago
+          if (c >= 1) {
+            mbar_wait(free_bar + 8u * (sl ^ 1u), (free_par >> (sl ^ 1u)) & 1u);
+            free_par ^= 1u << (sl ^ 1u);
+          }
+          tc_fence_after();
+          issue_chunk(c + 1, (int)(sl ^ 1u), aslot);
+        }
+        math32(va);
+        math32(vb);
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       if constexpr (XT) {
@@ -418,16 +494,18 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
       tc_fence_after();
       uint32_t va[32], vb[32];
       tmem_ld32_issue(d_lane_s, va);
-#pragma unroll
-      for (int i = 0; i < CN / 32; ++i) {
-        uint32_t (&cur)[32] = (i & 1) ? vb : va;
-        uint32_t (&nxt)[32] = (i & 1) ? va : vb;
-        tmem_ld_wait();
-        if (i + 1 < CN / 32) {
-          tmem_ld32_issue(d_lane_s + (i + 1) * 32, nxt);
-        } else if (c + 1 < NCH) {
-          // the last columns of this chunk are in registers: the accumulator is free, so the MMA of the
-          // next chunk is issued now and runs under the arithmetic of this last block
+      // the accumulator is free once the LAST 32 columns of the chunk are in registers: then the MMA of the next chunk
+      // (or, XT, of the next tile) is issued.  EARLY: that moment is moved from the top of the last block to the middle
+      // of the second-to-last one (the last block's load is waited for after half of the previous block's arithmetic),
+      // so that 1.5 blocks of arithmetic instead of 1 cover the MMA latency (the wait for the MMA at the top of a chunk
+      // was 6.8 % of all warp samples in profiles/r02_nnedi3_*: the MMA was not done when the last block was).
+#ifndef MPVP_X_NN_EARLY
+#define MPVP_X_NN_EARLY 1
+#endif
+      constexpr int NB = CN / 32;
+      constexpr bool EARLY = MPVP_X_NN_EARLY && EPI == 3 && NB >= 2;
+      auto accumulator_free = [&]() {
+        if (c + 1 < NCH) {
           tc_fence_before();
           wg_barrier(wg);
           if (lt == 0) {
@@ -443,6 +521,17 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
             issue_chunk(0, 0, nxt_aslot);
           }
           prefetch_tile(nxt_tile + tile_step, ahead);   // the staging buffer was last read by front_build above
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        uint32_t (&cur)[32] = (i & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (i & 1) ? va : vb;
+        if (!(EARLY && i == NB - 1)) tmem_ld_wait();   // EARLY: the last block was waited for inside the previous one
+        if (i + 1 < NB) {
+          tmem_ld32_issue(d_lane_s + (i + 1) * 32, nxt);
+        } else if (!EARLY) {
+          accumulator_free();
         }
         // registers 0..15: softmax logits of 16 neurons, 16..31: their elliott inputs
         if constexpr (EPI == 3) {
@@ -474,6 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
             rn = __fmul2_rn(rn, __ffma2_rn(den, rn, make_float2(2.f, 2.f)));
             vsum2 = __ffma2_rn(num, rn, vsum2);   // accumulates -vsum
             wsum2 = __fadd2_rn(wsum2, __fadd2_rn(__fadd2_rn(s1[0], s1[1]), __fadd2_rn(s1[2], s1[3])));
+            if (EARLY && g == 0 && i == NB - 2) {
+              tmem_ld_wait();        // the chunk's last 32 columns (issued at the top of this block) are in registers
+              accumulator_free();
+            }
           }
         } else if constexpr (EPI == 2) {
           // packed f32x2: two neurons per instruction on the FMA pipe
@@ -509,6 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
       }
     }
 
+    }   // !PP
     if constexpr (EPI == 2) {
       wsum = wsum2.x + wsum2.y;
       vsum = vsum2.x + vsum2.y;
@@ -595,7 +689,7 @@ int launch_tc(const NnTcArgs& a0, int device, cudaStream_t stream) {
   const bool use_tma = a0.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&tmap, a0.in, 4, a0.w, a0.h, a0.n, a0.in_sy, a0.in_sn, 40, SH);
   const int SW = use_tma ? 40 : (kTileW + HX - 1);
   const int STG = (SW * SH + 31) & ~31;
-  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * NA * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (3 * kWG + 1) + 16;
+  size_t smem = (size_t)KX * N * 2 + (size_t)kWG * NA * KX * 128 * 2 + sizeof(float) * kWG * STG + 8 * (5 * kWG + 1) + 16;
   // one CTA per SM: the kernel allocates all 512 TMEM columns
   if (smem < 120 * 1024) smem = 120 * 1024;
   NnTcArgs a = a0;
