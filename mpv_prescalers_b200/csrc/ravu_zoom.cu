@@ -148,6 +148,9 @@ __device__ __forceinline__ float key_luma709(float r, float g, float b) {
 // =====================================================================================================================
 // TEXF (opt-in): the LUT fetch is ONE texture instruction (hardware bilinear blend of the four binary16 texels with 8-bit
 // blend weights) instead of four gathered loads and the fp32 blend.
+#ifndef MPVP_X_ZOOM_POWT
+#define MPVP_X_ZOOM_POWT 0   // general path, anti-ringing: powers of the staged tile kept as float4 in shared memory (measured)
+#endif
 template <int R, int C, int KEYMODE, bool AR, bool LUTH, bool TEXF>
 __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ ZoomArgs A) {
   constexpr int N = 2 * R, TAPS = N * N, G = 4;
@@ -159,7 +162,9 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
   constexpr int NP = (C == 1) ? 1 : 4;                 // plane 0 = key plane, 1..3 = colours
   constexpr int RPT = kTOH / (kNT / kTOW);             // rows per thread
 
+  constexpr bool POWT = MPVP_X_ZOOM_POWT && AR && C == 1;   // anti-ringing powers once per staged source pixel instead of per output pixel and tap
   __shared__ float s_src[NP * PLANE];
+  __shared__ float4 s_pow[POWT ? PLANE : 1];
   __shared__ int s_key[CW * CH];
   __shared__ int s_bx[kTOW], s_by[kTOH];               // base texel - first base of the tile
   __shared__ int s_xi[kTOW][2 * B];                    // LUT texel column of (mirrored, blk)
@@ -223,7 +228,13 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
         const int64_t off = src0 + (int64_t)gy * A.in_sy + gx;
         const int d = sy * SWt + sx;
         if constexpr (C == 1) {
-          s_src[d] = load_px_t<FMT>(A.in, off, A.io.in_max);
+          const float v = load_px_t<FMT>(A.in, off, A.io.in_max);
+          s_src[d] = v;
+          if constexpr (POWT) {
+            const float cc = 0.1f + v, dd = 1.1f - v;
+            const float pc = pow32(cc), pd = pow32(dd);
+            s_pow[d] = make_float4(pc, pd, pc * cc, pd * dd);
+          }
         } else {
           const float c0 = load_px_t<FMT>(A.in, off, A.io.in_max);
           const float c1 = load_px_t<FMT>(A.in, off + A.in_sc, A.io.in_max);
@@ -315,12 +326,18 @@ __global__ void __launch_bounds__(kNT) ravu_zoom_kernel(const __grid_constant__ 
                 const float s = kb[(C == 1 ? 0 : (1 + c)) * PLANE + (t % N) * SWt + (t / N)];
                 res[c] = fmaf(s, wv[e], res[c]);
                 if constexpr (AR) {
-                  const float cc = 0.1f + s, dd = 1.1f - s;
-                  const float pc = pow32(cc), pd = pow32(dd);
-                  hi[c] = fmaf(pc, av[e], hi[c]);
-                  lo[c] = fmaf(pd, av[e], lo[c]);
-                  hi2[c] = fmaf(pc * cc, av[e], hi2[c]);
-                  lo2[c] = fmaf(pd * dd, av[e], lo2[c]);
+                  float4 pw;
+                  if constexpr (POWT) {
+                    pw = s_pow[cby * SWt + cbx + (t % N) * SWt + (t / N)];
+                  } else {
+                    const float cc = 0.1f + s, dd = 1.1f - s;
+                    const float pc = pow32(cc), pd = pow32(dd);
+                    pw = make_float4(pc, pd, pc * cc, pd * dd);
+                  }
+                  hi[c] = fmaf(pw.x, av[e], hi[c]);
+                  lo[c] = fmaf(pw.y, av[e], lo[c]);
+                  hi2[c] = fmaf(pw.z, av[e], hi2[c]);
+                  lo2[c] = fmaf(pw.w, av[e], lo2[c]);
                 }
               }
             }
