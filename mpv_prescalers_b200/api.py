@@ -547,6 +547,8 @@ def _prescale_generic(frames: torch.Tensor, hk: HookFile, output_size, lut_preci
     squeeze = x.dim() == 2
     if squeeze:
         x = x[None]
+    if output_size is None and any("3x" in (p.desc or "").lower() for p in hk.passes):
+        output_size = (3 * x.shape[-2], 3 * x.shape[-1])     # the natural target of a tripling hook (run() assumes 2x)
     res, off = gh.run(x, output_size, is_yuv)
     applied = tuple(res.shape) != tuple(x.shape) or off != (0.0, 0.0) or not torch.equal(res, x)
     if correct_offset and off != (0.0, 0.0):

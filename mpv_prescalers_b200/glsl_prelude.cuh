@@ -6,19 +6,36 @@
 
 typedef long long i64;
 
+struct ivec2;
 struct vec2 {
   float x, y;
   vec2() : x(0.f), y(0.f) {}
   explicit vec2(float s) : x(s), y(s) {}
+  explicit vec2(const ivec2& v);
   vec2(float a, float b) : x(a), y(b) {}
   float& operator[](int i) { return i == 0 ? x : y; }
   float operator[](int i) const { return i == 0 ? x : y; }
 };
+typedef unsigned int uint;
+struct uvec3 {   // the gl_* built-ins of a compute pass
+  uint x, y, z;
+  uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
+};
 struct ivec2 {
   int x, y;
   ivec2() : x(0), y(0) {}
+  explicit ivec2(int s) : x(s), y(s) {}
   ivec2(int a, int b) : x(a), y(b) {}
+  explicit ivec2(uvec3 v) : x((int)v.x), y((int)v.y) {}
+  explicit ivec2(vec2 v) : x((int)v.x), y((int)v.y) {}
 };
+inline vec2::vec2(const ivec2& v) : x((float)v.x), y((float)v.y) {}
+inline ivec2 operator+(ivec2 a, ivec2 b) { return ivec2(a.x + b.x, a.y + b.y); }
+inline ivec2 operator-(ivec2 a, ivec2 b) { return ivec2(a.x - b.x, a.y - b.y); }
+inline ivec2 operator*(ivec2 a, ivec2 b) { return ivec2(a.x * b.x, a.y * b.y); }
+inline ivec2 operator+(ivec2 a, int b) { return ivec2(a.x + b, a.y + b); }
+inline ivec2 operator-(ivec2 a, int b) { return ivec2(a.x - b, a.y - b); }
+inline ivec2 operator*(ivec2 a, int b) { return ivec2(a.x * b, a.y * b); }
 struct vec3 {
   float x, y, z;
   vec3() : x(0.f), y(0.f), z(0.f) {}
@@ -92,6 +109,11 @@ GLSL_VEC_OPS(vec2, 2)
 GLSL_VEC_OPS(vec3, 3)
 GLSL_VEC_OPS(vec4, 4)
 
+// compute-pass synchronisation
+inline void barrier() { __syncthreads(); }
+inline void groupMemoryBarrier() { __threadfence_block(); }
+inline void memoryBarrierShared() { __threadfence_block(); }
+
 // scalar built-ins (GLSL names)
 inline float fract(float a) { return a - floorf(a); }
 inline float floor(float a) { return floorf(a); }
@@ -112,6 +134,7 @@ inline float intBitsToFloat(int v) { return __int_as_float(v); }
 struct mat4x3 {   // 4 columns of vec3
   vec3 c[4];
   mat4x3() {}
+  explicit mat4x3(float s) { c[0] = vec3(s, 0.f, 0.f); c[1] = vec3(0.f, s, 0.f); c[2] = vec3(0.f, 0.f, s); c[3] = vec3(0.f); }   // GLSL: s on the diagonal
   mat4x3(vec3 a, vec3 b, vec3 d, vec3 e) { c[0] = a; c[1] = b; c[2] = d; c[3] = e; }
   vec3& operator[](int i) { return c[i]; }
   vec3 operator[](int i) const { return c[i]; }

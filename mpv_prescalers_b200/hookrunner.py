@@ -11,7 +11,9 @@ form") still runs on the GPU, and it doubles as an on-device cross-check of the 
 
 Supported: fragment passes (``vec4 hook()``), helper functions, ``#define`` macros, the types / built-ins listed in
 ``glsl_prelude.cuh``, ``NAME_tex / NAME_texOff / NAME_pos / NAME_size / NAME_pt / NAME_raw / NAME_mul``,
-``texture(lut, vec2)``, ``textureGatherOffset``.  Not supported (raises ``HookError``): compute passes (``//!COMPUTE``).
+``texture(lut, vec2)``, ``textureGatherOffset``, and compute passes (``//!COMPUTE bw bh [tw th]``: ``shared`` arrays,
+``barrier()``, the ``gl_*InvocationID`` / ``gl_WorkGroup*`` built-ins, ``imageStore(out_image, ...)``, ``NAME_map``): one
+CUDA block per work group, the shader's own shared-memory staging and thread mapping kept as written.
 There is no CPU fallback; nothing here imports ``oracle/``.
 """
 from __future__ import annotations
@@ -62,16 +64,38 @@ def _convert_functions(lines: List[str]) -> List[str]:
     return out
 
 
+_SHARED_DECL = re.compile(r"^\s*shared\s+(float|vec2|vec3|vec4)\s+([A-Za-z_]\w*)\s*\[\s*(\d+)\s*\]\s*;\s*$")
+_SHARED_WORDS = {"float": 1, "vec2": 2, "vec3": 3, "vec4": 4}
+
+
+def _convert_shared(lines: List[str]) -> List[str]:
+    """``shared T name[n];`` -> raw ``__shared__`` storage plus a typed pointer (the vector types have constructors, which
+    CUDA does not allow on ``__shared__`` objects)."""
+    out = []
+    for ln in lines:
+        m = _SHARED_DECL.match(ln)
+        if m:
+            t, name, n = m.group(1), m.group(2), int(m.group(3))
+            out.append(f"__shared__ float _sh_{name}[{n * _SHARED_WORDS[t]}]; {t}* const {name} = reinterpret_cast<{t}*>(_sh_{name});")
+        elif re.match(r"^\s*shared\b", ln):
+            raise HookError(f"unsupported shared declaration: {ln.strip()!r}")
+        else:
+            out.append(ln)
+    return out
+
+
 def transpile_pass(p: Pass, index: int, bound: List[str]) -> str:
-    """CUDA source of one fragment pass: ``extern "C" __global__ void pass_<index>(...)``."""
-    if p.compute:
-        raise HookError(f"pass {p.desc!r}: compute passes (//!COMPUTE) are not supported by the generic runner")
+    """CUDA source of one pass: ``extern "C" __global__ void pass_<index>(...)``.  Fragment passes (``vec4 hook()``) run one
+    thread per output texel; compute passes (``void hook()`` + ``imageStore``) run one block per work group."""
     body = p.body
-    if "vec4 hook()" not in body:
-        raise HookError(f"pass {p.desc!r}: no `vec4 hook()` entry point")
+    entry = "void hook()" if p.compute else "vec4 hook()"
+    if entry not in body:
+        raise HookError(f"pass {p.desc!r}: no `{entry}` entry point")
     body = _FLOAT_LIT.sub(lambda m: m.group(1) + "f", body)
     body = _SWIZZLE.sub(lambda m: "." + m.group(1) + "()", body)
     lines = _convert_functions(body.split("\n"))
+    if p.compute:
+        lines = _convert_shared(lines)
     macros = []
     for k, name in enumerate(bound):
         macros += [
@@ -82,30 +106,52 @@ def transpile_pass(p: Pass, index: int, bound: List[str]) -> str:
             f"#define {name}_mul 1.0f",
             f"#define {name}_tex(p) tex_sample(_tex[{k}], _frame, (p))",
             f"#define {name}_texOff(o) tex_sample(_tex[{k}], _frame, _pos + {name}_pt * (o))",
+            f"#define {name}_map(id) _texmap(id)",
             f"#define {name} (_tex[{k}])",
         ]
-    undef = [f"#undef {name}{sfx}" for name in bound for sfx in ("_raw", "_pos", "_size", "_pt", "_mul", "_tex", "_texOff", "")]
+    undef = [f"#undef {name}{sfx}" for name in bound for sfx in ("_raw", "_pos", "_size", "_pt", "_mul", "_tex", "_texOff", "_map", "")]
     # user macros must not leak into the next pass
     user = re.findall(r"^\s*#define\s+([A-Za-z_]\w*)", p.body, flags=re.M)
     undef += [f"#undef {u}" for u in user]
-    src = [
+    head = [
         f"// pass {index}: {p.desc}",
         *macros,
         "#define texture(t, c) tex_sample((t), _frame, (c))",
         "#define textureGatherOffset(t, c, o, comp) tex_gather((t), _frame, (c), (o), (comp))",
         f'extern "C" __global__ void pass_{index}(const Tex* __restrict__ _tex, float* __restrict__ _out, int _ow, int _oh, int _oc, int _n) {{',
         "  const int _ox = blockIdx.x * blockDim.x + threadIdx.x, _oy = blockIdx.y * blockDim.y + threadIdx.y, _frame = blockIdx.z;",
-        "  if (_ox >= _ow || _oy >= _oh) return;",
-        "  const vec2 _pos = vec2(((float)_ox + 0.5f) / (float)_ow, ((float)_oy + 0.5f) / (float)_oh);",
-        *lines,
-        "  const vec4 _r = hook();",
-        "  float* _q = _out + ((i64)_frame * _oh + _oy) * (i64)_ow * _oc + (i64)_ox * _oc;",
-        "  _q[0] = _r.x; if (_oc > 1) _q[1] = _r.y; if (_oc > 2) _q[2] = _r.z; if (_oc > 3) _q[3] = _r.w;",
-        "}",
-        "#undef texture",
-        "#undef textureGatherOffset",
-        *undef,
     ]
+    if p.compute:
+        # every thread of the work group stays alive (barrier()); out-of-range imageStore()s are dropped like the host does.
+        # NAME_map(id): output texel -> normalised coordinate, (id + 0.5) * (1 / output size) as the host's prelude defines it
+        kernel = [
+            "  const uvec3 gl_WorkGroupID(blockIdx.x, blockIdx.y, 0u), gl_WorkGroupSize(blockDim.x, blockDim.y, 1u);",
+            "  const uvec3 gl_LocalInvocationID(threadIdx.x, threadIdx.y, 0u), gl_GlobalInvocationID((uint)_ox, (uint)_oy, 0u);",
+            "  const uint gl_LocalInvocationIndex = threadIdx.y * blockDim.x + threadIdx.x;",
+            "  const vec2 _pos = vec2(((float)_ox + 0.5f) / (float)_ow, ((float)_oy + 0.5f) / (float)_oh);",
+            "  const vec2 _out_scale = vec2(1.0f / (float)_ow, 1.0f / (float)_oh);",
+            "  auto _texmap = [&](ivec2 id) -> vec2 { return (vec2(id) + vec2(0.5f)) * _out_scale; };",
+            "  const int out_image = 0;",
+            "  auto imageStore = [&](int, ivec2 _p, vec4 _r) {",
+            "    if (_p.x < 0 || _p.y < 0 || _p.x >= _ow || _p.y >= _oh) return;",
+            "    float* _q = _out + ((i64)_frame * _oh + _p.y) * (i64)_ow * _oc + (i64)_p.x * _oc;",
+            "    _q[0] = _r.x; if (_oc > 1) _q[1] = _r.y; if (_oc > 2) _q[2] = _r.z; if (_oc > 3) _q[3] = _r.w;",
+            "  };",
+            *lines,
+            "  hook();",
+            "}",
+        ]
+    else:
+        kernel = [
+            "  if (_ox >= _ow || _oy >= _oh) return;",
+            "  const vec2 _pos = vec2(((float)_ox + 0.5f) / (float)_ow, ((float)_oy + 0.5f) / (float)_oh);",
+            *lines,
+            "  const vec4 _r = hook();",
+            "  float* _q = _out + ((i64)_frame * _oh + _oy) * (i64)_ow * _oc + (i64)_ox * _oc;",
+            "  _q[0] = _r.x; if (_oc > 1) _q[1] = _r.y; if (_oc > 2) _q[2] = _r.z; if (_oc > 3) _q[3] = _r.w;",
+            "}",
+        ]
+    src = head + kernel + ["#undef texture", "#undef textureGatherOffset", *undef]
     return "\n".join(src) + "\n"
 
 
@@ -238,12 +284,19 @@ class GenericHook:
                     desc[i, 2] = (linear << 32) | tc
                     desc[i, 3] = sn
                 d_desc = torch.from_numpy(desc).to(dev)
-                out = torch.empty((n, ph, pw, comps), dtype=torch.float32, device=dev)
+                if p.compute:   # //!COMPUTE bw bh [tw th]: one work group per bw x bh output block, tw x th threads
+                    bw, bh = p.compute[0], p.compute[1]
+                    tw, th = (p.compute[2], p.compute[3]) if len(p.compute) >= 4 else (bw, bh)
+                    grid, block = ((pw + bw - 1) // bw, (ph + bh - 1) // bh, n), (tw, th, 1)
+                    out = torch.zeros((n, ph, pw, comps), dtype=torch.float32, device=dev)
+                else:
+                    grid, block = ((pw + 31) // 32, (ph + 7) // 8, n), (32, 8, 1)
+                    out = torch.empty((n, ph, pw, comps), dtype=torch.float32, device=dev)
                 args = [np.array([d_desc.data_ptr()], dtype=np.uint64), np.array([out.data_ptr()], dtype=np.uint64),
                         np.array([pw], dtype=np.int32), np.array([ph], dtype=np.int32), np.array([comps], dtype=np.int32),
                         np.array([n], dtype=np.int32)]
                 argp = np.array([a.ctypes.data for a in args], dtype=np.uint64)
-                _check(driver.cuLaunchKernel(fns[k], (pw + 31) // 32, (ph + 7) // 8, n, 32, 8, 1, 0, stream, argp.ctypes.data, 0), f"launch of pass {k}")
+                _check(driver.cuLaunchKernel(fns[k], *grid, *block, 0, stream, argp.ctypes.data, 0), f"launch of pass {k}")
                 torch.cuda.current_stream(dev).synchronize()  # keeps d_desc / args alive; this is the slow general path
                 if p.save:
                     saved[p.save] = out

@@ -1,5 +1,5 @@
-"""LUT trainer for the RAVU-Lite family: the piece of the absent upstream ``source`` branch
-(``README.md:3-4``) that produces a ``//!TEXTURE`` weight LUT from example images.
+"""LUT trainer for the single-pass RAVU families, RAVU-Lite and RAVU-3x: the piece of the
+absent upstream ``source`` branch (``README.md:3-4``) that produces a ``//!TEXTURE`` weight LUT from example images.
 
 RAVU is "rapid and accurate" learned upscaling: the 2x2 output pixels of every source pixel are a linear filter of the
 source window, with one filter per (angle, strength, coherence) bucket of the window's structure tensor
@@ -9,7 +9,10 @@ pixels.  The shipped LUTs are point-symmetric -- tap ``N-1-t`` of phase ``c`` ca
 ``3-c``, which is what lets the shader store half the taps and fetch ``w.wzyx`` for the mirrored one
 (``ravu-lite-r3.hook:97-118``; verified on the shipped payloads: centre texel ``.x == .w``, ``.y == .z`` exactly) -- so
 each bucket is solved for two weight vectors ``W_0, W_1`` on the data augmented with its 180-degree rotation, and
-``W_3 = reverse(W_0)``, ``W_2 = reverse(W_1)``.
+``W_3 = reverse(W_0)``, ``W_2 = reverse(W_1)``.  RAVU-3x has the same structure with a 3x3 block of output pixels: the
+centre is the source pixel itself, the other eight are filters ``W_0..W_7`` in output order, stored as two texels per tap
+(``res0`` / ``res1``), with ``W_{7-p} = reverse(W_p)`` (``compute/ravu-3x-r2.hook:84-114``: the mirrored tap reads
+``w1.wzyx`` into ``res0`` and ``w0.wzyx`` into ``res1``), so four weight vectors are solved per bucket.
 
 Everything runs on the GPU: the buckets come from the same CUDA key kernel the hook uses at run time
 (``prescale(..., return_buckets=True)``), the normal equations are accumulated per bucket in float64, and the result is
@@ -29,7 +32,7 @@ import torch
 
 from .hookfile import HookError, HookFile
 
-__all__ = ["train_ravu_lite", "write_hook_with_lut", "lut_to_hex"]
+__all__ = ["train_ravu", "train_ravu_lite", "write_hook_with_lut", "lut_to_hex"]
 
 
 def _windows(lr: torch.Tensor, radius: int) -> torch.Tensor:
@@ -44,42 +47,50 @@ def _windows(lr: torch.Tensor, radius: int) -> torch.Tensor:
     return torch.stack(cols, dim=1)
 
 
-def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: float = 1e-9, min_samples: Optional[int] = None,
-                    exclude_clipped: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """Least-squares LUT of a RAVU-Lite hook from training pairs.
+def train_ravu(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: float = 1e-9, min_samples: Optional[int] = None,
+               exclude_clipped: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Least-squares LUT of a RAVU-Lite or (luma) RAVU-3x hook from training pairs.
 
-    hook   a ``ravu-lite(-ar)-rN.hook``: its key constants decide the buckets, its LUT fills buckets that see too few samples;
-    lr     ``[F, H, W]`` float32 CUDA planes in [0, 1];  hr  ``[F, 2H, 2W]``: the true 2x planes, centre-aligned like the
-           shader's output (phase c of source pixel (x, y) is hr[2y + c % 2, 2x + c // 2], ``ravu-lite-r3.hook:128-134``);
+    hook   a ``ravu-lite(-ar)-rN.hook`` or ``compute/ravu-3x-rN.hook``: its key constants decide the buckets, its LUT fills
+           buckets that see too few samples;
+    lr     ``[F, H, W]`` float32 CUDA planes in [0, 1];  hr  ``[F, sH, sW]`` (s = 2 or 3): the true planes, aligned like the
+           shader's output (output pixel (i, j) of source pixel (x, y) is hr[s*y + j, s*x + i]; ``ravu-lite-r3.hook:128-134``,
+           ``compute/ravu-3x-r2.hook:106-114``);
     ridge  Tikhonov term relative to the mean diagonal of the normal matrix;
     exclude_clipped  drop source pixels with a target at exactly 0 or 1 (the shader clamps its result to [0, 1], which
            makes such pixels uninformative about the linear filter).
 
-    Returns ``(lut [288, LW, 4] float32, samples_per_bucket [288])``."""
+    Returns ``(lut [rows, LW, 4] float32, samples_per_bucket [rows])``."""
     from .api import prescale
 
     v = hook.variant
-    if v.family != "ravu-lite":
-        raise HookError("train_ravu_lite() trains the RAVU-Lite family")
+    if v.family not in ("ravu-lite", "ravu-3x") or v.plane != "luma":
+        raise HookError("train_ravu() trains the single-pass luma families: ravu-lite(-ar)-rN and ravu-3x-rN "
+                        "(the -yuv / -rgb files of ravu-3x apply the same LUT per channel)")
     if lr.device.type != "cuda" or hr.device.type != "cuda":
         raise ValueError("training planes must be CUDA tensors")
+    S = 2 if v.family == "ravu-lite" else 3
     f, h, w = lr.shape
-    if tuple(hr.shape) != (f, 2 * h, 2 * w):
-        raise ValueError(f"hr must be {(f, 2 * h, 2 * w)}, got {tuple(hr.shape)}")
+    if tuple(hr.shape) != (f, S * h, S * w):
+        raise ValueError(f"hr must be {(f, S * h, S * w)}, got {tuple(hr.shape)}")
     r = v.radius
     n = 2 * r - 1
     N, half = n * n, (n * n - 1) // 2
-    rows = 288
+    rows = int(v.lut.height)
+    # trained output pixels in the LUT's phase order p (lite: all four; 3x: the eight around the copied centre), q = i*S + j
+    cells = [q for q in range(S * S) if not (S == 3 and q == 4)]
+    P, U = len(cells), len(cells) // 2           # phases, unknown weight vectors (W_{P-1-p} = reverse(W_p))
     dev = lr.device
     A = torch.zeros((rows, N, N), dtype=torch.float64, device=dev)
-    B = torch.zeros((rows, N, 2), dtype=torch.float64, device=dev)
+    B = torch.zeros((rows, N, U), dtype=torch.float64, device=dev)
     count = torch.zeros(rows, dtype=torch.int64, device=dev)
     rev = torch.arange(N - 1, -1, -1, device=dev)
-    _, buckets = prescale(lr, hook, return_buckets=True)       # the hook's own key kernel
+    out_size = None if S == 2 else (S * h, S * w)
+    _, buckets = prescale(lr, hook, out_size, return_buckets=True)       # the hook's own key kernel
     for k in range(f):
         X = _windows(lr[k], r)                                   # [P, N]
         H = hr[k]
-        Y = torch.stack([H[0::2, 0::2], H[1::2, 0::2], H[0::2, 1::2], H[1::2, 1::2]], dim=-1).reshape(-1, 4)   # phases 0..3
+        Y = torch.stack([H[(q % S)::S, (q // S)::S] for q in cells], dim=-1).reshape(-1, P)
         b = buckets[k].reshape(-1).long()
         if exclude_clipped:
             keep = ((Y > 0.0) & (Y < 1.0)).all(dim=1)
@@ -95,10 +106,9 @@ def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: f
             yb = Y[s:s + m].double()
             xr = xb[:, rev]                                      # the window rotated by 180 degrees
             A[row] += xb.T @ xb + xr.T @ xr
-            # W_0 sees (x, y_0) and (rev x, y_3); W_1 sees (x, y_1) and (rev x, y_2)
-            B[row, :, 0] += xb.T @ yb[:, 0] + xr.T @ yb[:, 3]
-            B[row, :, 1] += xb.T @ yb[:, 1] + xr.T @ yb[:, 2]
-    lut_old = np.asarray(v.lut.data, dtype=np.float32)           # [288, LW, 4]
+            # W_p sees (x, y_p) and (rev x, y_{P-1-p})
+            B[row] += xb.T @ yb[:, :U] + xr.T @ yb[:, P - 1 - torch.arange(U, device=dev)]
+    lut_old = np.asarray(v.lut.data, dtype=np.float32)           # [rows, LW, 4]
     lut = lut_old.copy()
     need = (4 * N) if min_samples is None else int(min_samples)
     count_h = count.cpu().numpy()
@@ -108,11 +118,23 @@ def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: f
             continue                                             # too few samples: the hook's own row stays
         a = A[row]
         lam = ridge * float(torch.diagonal(a).mean())
-        Wsol = torch.linalg.solve(a + lam * eye, B[row]).cpu().numpy()   # [N, 2] = (W_0, W_1)
-        W0, W1 = Wsol[:, 0], Wsol[:, 1]
+        Wsol = torch.linalg.solve(a + lam * eye, B[row]).cpu().numpy()   # [N, U]
+        Wfull = np.concatenate([Wsol, Wsol[::-1, ::-1]], axis=1)         # [N, P]: W_{P-1-p}[t] = W_p[N-1-t]
         for t in range(half + 1):
-            lut[row, t] = (W0[t], W1[t], W1[N - 1 - t], W0[N - 1 - t])
+            if S == 2:
+                lut[row, t] = Wfull[t]
+            else:                                                # two texels per tap: res0 = phases 0..3, res1 = phases 4..7
+                lut[row, 2 * t] = Wfull[t, :4]
+                lut[row, 2 * t + 1] = Wfull[t, 4:]
     return lut.astype(np.float32), count_h
+
+
+def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: float = 1e-9, min_samples: Optional[int] = None,
+                    exclude_clipped: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """:func:`train_ravu` restricted to the RAVU-Lite family (the round-2 entry point; kept for callers)."""
+    if hook.variant.family != "ravu-lite":
+        raise HookError("train_ravu_lite() trains the RAVU-Lite family")
+    return train_ravu(hook, lr, hr, ridge, min_samples, exclude_clipped)
 
 
 def lut_to_hex(lut: np.ndarray) -> str:

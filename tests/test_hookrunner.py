@@ -8,7 +8,9 @@ import pytest
 from tests.conftest import hook_path
 
 COMPILE = ["ravu-lite-ar-r3.hook", "ravu-r2.hook", "ravu-r2-rgb.hook", "ravu-zoom-ar-r2-rgb.hook", "gather/ravu-lite-ar-r2.hook",
-           "gather/ravu-r3.hook", "nnedi3-nns16-win8x4.hook", "gather/nnedi3-nns16-win8x4.hook", "ravu-zoom-r3.hook"]
+           "gather/ravu-r3.hook", "nnedi3-nns16-win8x4.hook", "gather/nnedi3-nns16-win8x4.hook", "ravu-zoom-r3.hook",
+           "compute/ravu-lite-r2.hook", "compute/ravu-lite-ar-r3.hook", "compute/ravu-r3-rgb.hook", "compute/ravu-3x-r2.hook",
+           "compute/ravu-3x-r3-rgb.hook", "compute/ravu-zoom-r2.hook", "compute/nnedi3-nns16-win8x4.hook"]
 
 
 @pytest.mark.parametrize("name", COMPILE)
@@ -22,12 +24,26 @@ def test_hook_transpiles_and_compiles_for_sm100a(name):
     assert re.search(r"(?<![\w.])\d+\.\d+(?:[eE][-+]?\d+)?(?![\w.])", body) is None   # every literal became float32
 
 
-def test_compute_passes_are_refused():
+def test_compute_pass_keeps_the_shaders_own_work_group_structure():
+    """//!COMPUTE passes: shared arrays become raw __shared__ storage, barrier() a block barrier, imageStore a bounds-checked
+    store; every thread of the work group reaches the barrier (no early return)."""
+    from mpv_prescalers_b200 import HookFile
+    from mpv_prescalers_b200.hookrunner import GenericHook
+
+    gh = GenericHook(HookFile.parse(hook_path("compute/ravu-lite-r2.hook")))
+    body = gh.source.split("// pass 0")[1]
+    assert "__shared__ float _sh_inp[340];" in body and "barrier();" in body and "imageStore(out_image" in body
+    assert "if (_ox >= _ow || _oy >= _oh) return;" not in body
+    assert re.search(r"^\s*shared\b", body, flags=re.M) is None
+
+
+def test_unsupported_shared_declaration_is_refused():
     from mpv_prescalers_b200 import HookError, HookFile
     from mpv_prescalers_b200.hookrunner import GenericHook
 
-    with pytest.raises(HookError, match="compute"):
-        GenericHook(HookFile.parse(hook_path("compute/ravu-lite-r2.hook")))
+    text = open(hook_path("compute/ravu-lite-r2.hook")).read().replace("shared float inp[340];", "shared int inp[340];")
+    with pytest.raises(HookError, match="shared"):
+        GenericHook(HookFile.parse_text(text))
 
 
 def _modified_hook_text():
@@ -49,7 +65,9 @@ torch = pytest.importorskip("torch")
 
 RUN = [("ravu-lite-ar-r3.hook", None), ("ravu-r3.hook", None), ("ravu-r2-rgb.hook", None), ("ravu-r2-yuv.hook", None),
        ("ravu-zoom-ar-r2.hook", (96, 72)), ("nnedi3-nns16-win8x4.hook", None), ("gather/ravu-lite-ar-r2.hook", None),
-       ("gather/ravu-r3.hook", None), ("gather/nnedi3-nns16-win8x4.hook", None)]
+       ("gather/ravu-r3.hook", None), ("gather/nnedi3-nns16-win8x4.hook", None), ("compute/ravu-lite-r2.hook", None),
+       ("compute/ravu-lite-ar-r3.hook", None), ("compute/ravu-r3-rgb.hook", None), ("compute/ravu-3x-r2.hook", None),
+       ("compute/ravu-3x-r3-rgb.hook", None), ("compute/nnedi3-nns16-win8x4.hook", None)]
 
 
 def _close(got, ref, what):
@@ -119,8 +137,10 @@ def test_generic_runner_cross_checks_the_fused_kernels():
     if not torch.cuda.is_available():
         pytest.fail("no CUDA device")
     x = torch.from_numpy(batch(2, 1, 135, 240, config=83)[:, 0]).cuda()
-    for name in ("ravu-lite-ar-r3.hook", "ravu-r4.hook", "nnedi3-nns32-win8x6.hook"):
-        a = prescale(x, hook_path(name)).cpu().numpy()
-        b = prescale(x, hook_path(name), runner="generic").cpu().numpy()
+    for name, osz in (("ravu-lite-ar-r3.hook", None), ("ravu-r4.hook", None), ("nnedi3-nns32-win8x6.hook", None),
+                      ("compute/ravu-3x-r4.hook", None), ("compute/ravu-zoom-r2.hook", (311, 541))):
+        # (the compute flavour of ravu-zoom maps output texels through NAME_map(id), which the CPU interpreter does not model)
+        a = prescale(x, hook_path(name), output_size=osz).cpu().numpy()
+        b = prescale(x, hook_path(name), output_size=osz, runner="generic").cpu().numpy()
         d = np.abs(a - b)
         assert psnr(a, b) >= 60.0 and np.mean(d > 1e-3) <= 2e-4, f"{name}: {np.mean(d > 1e-3):.2e} of pixels differ, PSNR {psnr(a, b):.1f}"

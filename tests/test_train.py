@@ -24,7 +24,7 @@ def test_lut_hex_round_trip_and_hook_rewrite(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ravu-lite-r3.hook", "ravu-lite-r2.hook"])
+@pytest.mark.parametrize("name", ["ravu-lite-r3.hook", "ravu-lite-r2.hook", "compute/ravu-3x-r2.hook", "compute/ravu-3x-r3.hook"])
 def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
     """Self-consistency: high-resolution targets produced by a shipped LUT are a per-bucket LINEAR function of the source
     windows, so least squares must give that LUT back (well-populated buckets), and the retrained hook file must
@@ -33,7 +33,7 @@ def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
 
     from mpv_prescalers_b200 import HookFile, prescale
     from mpv_prescalers_b200.synth import batch
-    from mpv_prescalers_b200.train import train_ravu_lite, write_hook_with_lut
+    from mpv_prescalers_b200.train import train_ravu, write_hook_with_lut
     from tests.parity import psnr
 
     if not torch.cuda.is_available():
@@ -44,7 +44,7 @@ def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
     x = np.clip(0.2 + 0.6 * x + rng.normal(0, 0.04, x.shape), 0.02, 0.98).astype(np.float32)   # full-rank windows, few clipped targets
     lr = torch.from_numpy(x).cuda()
     hr = prescale(lr, hk)
-    lut, count = train_ravu_lite(hk, lr, hr)
+    lut, count = train_ravu(hk, lr, hr)
     ref = np.asarray(hk.variant.lut.data, np.float32).astype(np.float16).astype(np.float32)      # what the kernels apply
     well = count >= 5000
     assert well.sum() >= 20, f"only {well.sum()} well-populated buckets"
@@ -56,3 +56,18 @@ def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
     fresh = torch.from_numpy(np.clip(0.2 + 0.6 * batch(1, 1, 200, 300, config=92)[:, 0], 0, 1).astype(np.float32)).cuda()
     a, b = prescale(fresh, hk), prescale(fresh, str(out))
     assert psnr(a.cpu().numpy(), b.cpu().numpy()) >= 60.0
+
+
+def test_trainer_refuses_families_it_does_not_cover():
+    pytest.importorskip("torch")
+    import torch
+
+    from mpv_prescalers_b200 import HookError, HookFile
+    from mpv_prescalers_b200.train import train_ravu, train_ravu_lite
+
+    z = torch.zeros((1, 4, 4))
+    for name in ("ravu-r2.hook", "ravu-zoom-r2.hook", "compute/ravu-3x-r2-rgb.hook"):
+        with pytest.raises(HookError, match="single-pass luma"):
+            train_ravu(HookFile.parse(hook_path(name)), z, z)
+    with pytest.raises(HookError, match="RAVU-Lite"):
+        train_ravu_lite(HookFile.parse(hook_path("compute/ravu-3x-r2.hook")), z, z)

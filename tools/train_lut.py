@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Train a RAVU-Lite LUT on the GPU and write it as a complete hook file.
+"""Train a RAVU-Lite or RAVU-3x LUT on the GPU and write it as a complete hook file.
 
     python tools/train_lut.py --hook ravu-lite-r3.hook --hr planes.npy --out my-ravu-lite-r3.hook
+    python tools/train_lut.py --hook compute/ravu-3x-r3.hook --hr planes.npy --out my-ravu-3x-r3.hook
 
-``planes.npy``: float32 [F, 2H, 2W] high-resolution luma planes in [0, 1]; the low-resolution training input is their
-2x2 box average (the usual RAVU training degradation).  Without --hr a synthetic set is used (a smoke run: the result
+``planes.npy``: float32 [F, sH, sW] high-resolution luma planes in [0, 1] (s = 2, or 3 for ravu-3x); the low-resolution
+training input is their s x s box average (the usual RAVU training degradation).  Without --hr a synthetic set is used (a smoke run: the result
 is a valid filter for synthetic statistics, not a replacement of the shipped weights).
 """
 import argparse
@@ -17,7 +18,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpv_prescalers_b200 import HookFile, find_hook, prescale  # noqa: E402
 from mpv_prescalers_b200.synth import batch  # noqa: E402
-from mpv_prescalers_b200.train import train_ravu_lite, write_hook_with_lut  # noqa: E402
+from mpv_prescalers_b200.train import train_ravu, write_hook_with_lut  # noqa: E402
 
 
 def main():
@@ -29,13 +30,14 @@ def main():
     args = ap.parse_args()
     hk = HookFile.parse(find_hook(args.hook))
     hr = np.load(args.hr).astype(np.float32) if args.hr else batch(8, 1, 720, 960, config=7)[:, 0]
-    hr = torch.from_numpy(np.ascontiguousarray(hr[:, : hr.shape[1] // 2 * 2, : hr.shape[2] // 2 * 2])).cuda()
-    lr = (hr[:, 0::2, 0::2] + hr[:, 1::2, 0::2] + hr[:, 0::2, 1::2] + hr[:, 1::2, 1::2]) * 0.25
+    s = 3 if hk.variant.family == "ravu-3x" else 2
+    hr = torch.from_numpy(np.ascontiguousarray(hr[:, : hr.shape[1] // s * s, : hr.shape[2] // s * s])).cuda()
+    lr = torch.nn.functional.avg_pool2d(hr[:, None], s)[:, 0].contiguous()
     before = float(((prescale(lr, hk) - hr) ** 2).mean())
-    lut, count = train_ravu_lite(hk, lr, hr, ridge=args.ridge, exclude_clipped=False)
+    lut, count = train_ravu(hk, lr, hr, ridge=args.ridge, exclude_clipped=False)
     write_hook_with_lut(hk, lut, args.out)
     after = float(((prescale(lr, args.out) - hr) ** 2).mean())
-    print(f"{args.out}: {int((count >= 4 * lut.shape[1] * 2).sum())} of 288 buckets retrained on {int(count.sum())} windows; "
+    print(f"{args.out}: {int((count >= 4 * lut.shape[1] * 2).sum())} of {lut.shape[0]} buckets retrained on {int(count.sum())} windows; "
           f"training MSE {before:.3e} -> {after:.3e}")
 
 
