@@ -570,8 +570,11 @@ __device__ __forceinline__ void store_px_wb(void* __restrict__ p, int64_t off, f
 #endif
 constexpr int kStrip = MPVP_X_ZOOM_STRIP;
 constexpr int kPNT2 = kPTW * kPTH / kStrip;
+#ifndef MPVP_X_ZOOM_MINB
+#define MPVP_X_ZOOM_MINB 3   // resident CTAs per SM of the luma phase kernel (4 = 64 registers: measured)
+#endif
 template <int R, int C, bool AR, int SWT, bool MIX, bool TMA = false>
-__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : 3) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MPVP_X_ZOOM_MINB) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || (C == 1 && !AR && SWT > 0), "TMA staging: luma, no anti-ringing power tile, compile-time pitch");
   constexpr int kPNT = kPNT2;
   constexpr int N = 2 * R, TAPS = N * N;
