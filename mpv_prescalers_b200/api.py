@@ -634,13 +634,20 @@ def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: to
     if streams is None:
         streams = _host_streams[dev.index] = [torch.cuda.Stream(dev) for _ in range(2)]
     frame_bytes = c * (x.element_size() * h * w + out.element_size() * oh * ow)
-    chunk = max(1, min(n, (256 << 20) // max(frame_bytes, 1)))
+    # chunks of 32..256 MB, about ten per call: the first upload and the last download are the only copies nothing hides
+    chunk_bytes = min(256 << 20, max(32 << 20, n * frame_bytes // 10))
+    chunk = max(1, min(n, chunk_bytes // max(frame_bytes, 1)))
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
         for s in streams:
             s.wait_stream(cur)
-        for k, f0 in enumerate(range(0, n, chunk)):
-            f1 = min(n, f0 + chunk)
+        # the first chunks are small (an eighth, a quarter, a half of the steady size), so the download engine starts early
+        bounds, f0 = [], 0
+        while f0 < n:
+            step = max(1, chunk >> max(0, 3 - len(bounds)))
+            bounds.append((f0, min(n, f0 + step)))
+            f0 += step
+        for k, (f0, f1) in enumerate(bounds):
             s = streams[k & 1]
             with torch.cuda.stream(s):
                 xd = x[f0:f1].to(dev, non_blocking=True)
