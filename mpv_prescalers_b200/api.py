@@ -12,6 +12,7 @@ There is no CPU fallback: without a CUDA device or without the library this rais
 from __future__ import annotations
 
 import ctypes
+import dataclasses
 import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
@@ -634,6 +635,30 @@ def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: to
     if streams is None:
         streams = _host_streams[dev.index] = [torch.cuda.Stream(dev) for _ in range(2)]
     frame_bytes = c * (x.element_size() * h * w + out.element_size() * oh * ow)
+    bands = _host_row_bands(hk, n, c, h, oh, frame_bytes) if bks is None else None
+    if bands is not None:
+        # a few large luma frames: the pipeline's unit is a ROW BAND (plus the halo the kernels read, cropped after the
+        # launch -- the arithmetic of sharding.prescale_rowsplit, bit-identical to the whole frame), so that the copies
+        # of one band overlap the kernel of the next even when the call holds a single frame
+        sy = oh // h
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            for s in streams:
+                s.wait_stream(cur)
+            k = 0
+            for f in range(n):
+                for a, b, s0, s1 in bands:
+                    s = streams[k & 1]
+                    k += 1
+                    bpl = dataclasses.replace(pl, in_size=(s1 - s0, w), out_size=((s1 - s0) * sy, ow))
+                    with torch.cuda.stream(s):
+                        xd = x[f:f + 1, :, s0:s1, :].to(dev, non_blocking=True)          # contiguous rows of one plane
+                        od, _ = _launch(hk, bpl, xd, W, False, io)
+                        out[f:f + 1, :, a * sy:b * sy, :].copy_(od[:, :, (a - s0) * sy:(b - s0) * sy, :], non_blocking=True)
+                        del xd, od
+            for s in streams:
+                s.synchronize()
+        return out, None
     # chunks of 32..256 MB, about ten per call: the first upload and the last download are the only copies nothing hides
     chunk_bytes = min(256 << 20, max(32 << 20, n * frame_bytes // 10))
     chunk = max(1, min(n, chunk_bytes // max(frame_bytes, 1)))
@@ -659,6 +684,24 @@ def _prescale_host(hk: HookFile, pl: Plan, x: torch.Tensor, W: _Weights, dev: to
         for s in streams:
             s.synchronize()
     return out, bks
+
+
+_HOST_BAND_MIN_BYTES = 8 << 20   # a band moves at least this much over PCIe (in + out); tests lower it
+_HOST_BAND_CHUNKS = 16           # pipeline steps a call is cut into when it holds fewer frames than that
+
+
+def _host_row_bands(hk: HookFile, n: int, c: int, h: int, oh: int, frame_bytes: int):
+    """Row bands ``(a, b, s0, s1)`` (output rows of source rows [a, b) come from a launch on source rows [s0, s1)) for the
+    host pipeline, or None when whole frames already give it enough chunks.  Luma planes only (a band of one plane is one
+    contiguous piece of host memory); ravu-zoom is excluded like in the multi-GPU row split."""
+    from .sharding import row_bands
+
+    if c != 1 or hk.variant.family == "ravu-zoom" or oh % h != 0 or n >= _HOST_BAND_CHUNKS // 2 or h < 512:
+        return None
+    parts = min(-(-_HOST_BAND_CHUNKS // n), h // 256, max(1, frame_bytes // _HOST_BAND_MIN_BYTES))
+    if parts < 2:
+        return None
+    return [bd for bd in row_bands(h, parts) if bd[1] > bd[0]]
 
 
 def _bucket_shape(v: Variant, h: int, w: int, oh: int, ow: int) -> Tuple[int, ...]:

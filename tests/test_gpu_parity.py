@@ -582,6 +582,31 @@ def test_host_tensor_path_matches_device_path():
     assert host.device.type == "cpu" and torch.equal(dev, host)
 
 
+@pytest.mark.parametrize("name,n,h,w", [("nnedi3-nns32-win8x4.hook", 1, 1080, 640), ("nnedi3-nns16-win8x6.hook", 3, 600, 333),
+                                        ("ravu-lite-ar-r3.hook", 2, 1100, 500), ("ravu-r3.hook", 1, 2160, 256),
+                                        ("compute/ravu-3x-r2.hook", 1, 777, 300)])
+def test_host_path_row_bands_are_bit_identical(name, n, h, w, monkeypatch):
+    """A few large luma frames on the host are pipelined band by band (api._host_row_bands): same bits as the device call,
+    float32 and uint8 planes, caller-provided pinned destination."""
+    from mpv_prescalers_b200 import HookFile, api, prescale
+    from mpv_prescalers_b200.synth import batch
+
+    _need_gpu()
+    monkeypatch.setattr(api, "_HOST_BAND_MIN_BYTES", 1 << 16)
+    hk = HookFile.parse(hook_path(name))
+    s = 3 if "3x" in name else 2
+    for eb in (4, 1):
+        bands = api._host_row_bands(hk, n, 1, h, s * h, eb * h * w * (1 + s * s))
+        assert bands is not None and len(bands) >= 2      # the band path is what runs
+    x = torch.from_numpy(batch(n, 1, h, w, config=23))
+    dev = prescale(x.cuda(), hk)
+    out = torch.empty(tuple(dev.shape), dtype=torch.float32, pin_memory=True)
+    host = prescale(x.pin_memory(), hk, out=out)
+    assert host.device.type == "cpu" and torch.equal(dev.cpu(), host) and host.offset == dev.offset
+    raw = torch.round(x.clamp(0, 1) * 255).to(torch.uint8)
+    assert torch.equal(prescale(raw, hk), prescale(raw.cuda(), hk).cpu())
+
+
 def test_lut_precision_fp32_option():
     from mpv_prescalers_b200 import HookFile, prescale
     from mpv_prescalers_b200.synth import batch
