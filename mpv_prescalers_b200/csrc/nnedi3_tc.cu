@@ -43,7 +43,15 @@ struct NnTcArgs {
 };
 
 constexpr int kTileW = 32, kTileH = 4;  // 128 pixels = 128 TMEM lanes
-constexpr int kWG = 4;                  // warpgroups per CTA
+#ifndef MPVP_X_NN_WG
+#define MPVP_X_NN_WG 4
+#endif
+#ifndef MPVP_X_NN_PPW
+#define MPVP_X_NN_PPW 64   // ping-pong slot width (experiment: 128 with MPVP_X_NN_WG=2, i.e. 256 TMEM columns per warpgroup)
+#endif
+constexpr int kWG = MPVP_X_NN_WG;       // warpgroups per CTA
+constexpr int kWGCols = 512 / kWG;      // TMEM columns per warpgroup
+static_assert(2 * MPVP_X_NN_PPW <= kWGCols, "two ping-pong slots per warpgroup");
 constexpr int kThreads = 128 * kWG;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
 #ifndef MPVP_X_NN_PP
 #define MPVP_X_NN_PP 0
 #endif
-  constexpr bool PP = MPVP_X_NN_PP && N >= 128 && EPI == 3;
-  constexpr int CN = PP ? 64 : (N < 128 ? N : 128);     // columns per MMA chunk
+  constexpr bool PP = MPVP_X_NN_PP && N >= 2 * MPVP_X_NN_PPW && EPI == 3;
+  constexpr int CN = PP ? MPVP_X_NN_PPW : (N < 128 ? N : 128);     // columns per MMA chunk
   constexpr int NCH = N / CN;
   // Small networks (nns16 / nns32: one chunk of <= 64 columns per tile) keep TWO tiles in flight per warpgroup: the A
   // operand and the MMA of tile t+1 are issued before the epilogue of tile t starts (two A buffers, two TMEM slots,
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
   const uint32_t a_addr = smem_u32(my_a), b_addr = smem_u32(s_b);
   const uint32_t idesc = make_idesc(CN);
   const uint32_t my_mbar = smem_u32(s_mbar + 2 * wg);
-  const uint32_t d_col = tmem_base + (uint32_t)(wg * 128);
+  const uint32_t d_col = tmem_base + (uint32_t)(wg * kWGCols);
   const uint32_t d_lane = d_col + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;  // parity of this warpgroup's MMA-done barrier
   const uint32_t free_bar = smem_u32(s_mbar + 3 * kWG + 1 + 2 * wg);   // PP: [2] "slot loaded into registers by all four warps"
@@ -459,8 +467,13 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
         full_par ^= 1u << sl;
         tc_fence_after();
         uint32_t va[32], vb[32];
-        tmem_ld32_issue(d_lane + sl * 64u, va);
-        tmem_ld32_issue(d_lane + sl * 64u + 32u, vb);
+        [[maybe_unused]] uint32_t vc[32], vd[32];
+        tmem_ld32_issue(d_lane + sl * (uint32_t)CN, va);
+        tmem_ld32_issue(d_lane + sl * (uint32_t)CN + 32u, vb);
+        if constexpr (CN == 128) {
+          tmem_ld32_issue(d_lane + sl * (uint32_t)CN + 64u, vc);
+          tmem_ld32_issue(d_lane + sl * (uint32_t)CN + 96u, vd);
+        }
         tmem_ld_wait();
         // this warp's share of the slot is in registers
         tc_fence_before();
@@ -477,6 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
         }
         math32(va);
         math32(vb);
+        if constexpr (CN == 128) {
+          math32(vc);
+          math32(vd);
+        }
       }
     } else {
 #pragma unroll 1
