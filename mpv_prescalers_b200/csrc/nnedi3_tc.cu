@@ -544,6 +544,8 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
       for (int i = 0; i < NB; ++i) {
         uint32_t (&cur)[32] = (i & 1) ? vb : va;
         uint32_t (&nxt)[32] = (i & 1) ? va : vb;
+        // (tcgen05.wait::ld emits no instruction of its own: ptxas tracks the LDTM destination registers on the scoreboard,
+        // so WHERE the wait stands does not change the SASS -- only where accumulator_free() stands does)
         if (!(EARLY && i == NB - 1)) tmem_ld_wait();   // EARLY: the last block was waited for inside the previous one
         if (i + 1 < NB) {
           tmem_ld32_issue(d_lane_s + (i + 1) * 32, nxt);
