@@ -29,6 +29,24 @@ def batch(n: int, c: int, h: int, w: int, config: int = 0) -> np.ndarray:
     return out
 
 
+def natural(h: int, w: int, seed: int = 0, c: int = 1) -> np.ndarray:
+    """Natural-image statistics: 1/f amplitude spectrum with random phases, scaled to mean 0.5 and
+    standard deviation 0.18, clipped to [0, 1].  ``[h, w]`` (c == 1) or ``[c, h, w]`` with correlated channels."""
+    rng = np.random.default_rng(seed)
+    fy, fx = np.fft.fftfreq(h)[:, None], np.fft.rfftfreq(w)[None, :]
+    amp = 1.0 / np.maximum(np.sqrt(fx * fx + fy * fy), 1.0 / max(h, w))
+    amp[0, 0] = 0.0
+
+    def field():
+        spec = amp * np.exp(2j * np.pi * rng.random(amp.shape))
+        f = np.fft.irfft2(spec, s=(h, w))
+        return f / f.std()
+
+    base = field()
+    out = np.stack([np.clip(0.5 + 0.18 * (base if k == 0 else 0.8 * base + 0.6 * field()), 0.0, 1.0) for k in range(c)])
+    return out[0].astype(np.float32) if c == 1 else out.astype(np.float32)
+
+
 def pathological(h: int, w: int) -> dict:
     y, x = np.mgrid[0:h, 0:w]
     return {

@@ -48,7 +48,7 @@ def _quantise_planes(x, bits):
     return raw, (raw.astype(np.float32) / mx).astype(np.float32)
 
 
-def _run_ravu_variant(name, n, h, w, config, out_hw=None, in_bits=None):
+def _run_ravu_variant(name, n, h, w, config, out_hw=None, in_bits=None, planes=None, cascade_tol=1e-4):
     """in_bits: feed the kernel UNORM integer planes of that depth (uint8 / uint16) and ask for float32 output; the
     oracle runs on raw / (2**bits - 1), which is what HOOKED_tex() returns for such a plane."""
     from mpv_prescalers_b200 import HookFile, prescale
@@ -57,7 +57,7 @@ def _run_ravu_variant(name, n, h, w, config, out_hw=None, in_bits=None):
     _need_gpu()
     hk = HookFile.parse(hook_path(name))
     v = hk.variant
-    x = _frames(v, n, h, w, config)
+    x = _frames(v, n, h, w, config) if planes is None else planes(v)     # [n, channels, h, w]
     kw = {}
     if in_bits is None:
         xt = torch.from_numpy(x).cuda()
@@ -103,7 +103,7 @@ def _run_ravu_variant(name, n, h, w, config, out_hw=None, in_bits=None):
                 bad |= ~samek
                 counted |= ~samek & ~on_edge_mask(ref.keys[k], v)
             # exact-edge degeneracies (1-pixel-wide planes put every lattice key on the 135 degree edge) are not counted
-            assert counted.mean() <= 1e-4 or counted.sum() <= 3, f"{name}: {counted.mean():.2e} of pixels have a differing key"
+            assert counted.mean() <= cascade_tol or counted.sum() <= 3, f"{name}: {counted.mean():.2e} of pixels have a differing key"
             ok = ~_dilate(bad, v.radius + 1) if bad.any() else ~bad
             mask = np.repeat(np.repeat(ok, 2, 0), 2, 1)
         else:
@@ -544,6 +544,36 @@ def test_pathological_planes(name):
             assert d.max() <= 1e-3, f"{name} {pname}: flat plane not preserved ({d.max():.3e})"
         else:
             assert np.mean(d > 1e-3) <= 0.02 and psnr(np.nan_to_num(out), np.nan_to_num(ref)) >= 40.0, f"{name} {pname}"
+
+
+NATURAL_CASES = [("ravu-lite-ar-r3.hook", None), ("ravu-lite-r4.hook", None), ("ravu-r3.hook", None), ("ravu-r2-rgb.hook", None),
+                 ("compute/ravu-3x-r3.hook", None), ("ravu-zoom-r3.hook", (3, 3)), ("ravu-zoom-ar-r2.hook", (2.37, 2.11)),
+                 ("nnedi3-nns64-win8x6.hook", None), ("nnedi3-nns16-win8x4.hook", None)]
+
+
+@pytest.mark.parametrize("name,ratio", NATURAL_CASES)
+def test_natural_statistics_plane(name, ratio):
+    """A 1/f-spectrum plane (the statistics of real frames, far more low-strength / low-coherence buckets than
+    the band-limited mixture the other tests use), against the oracle with the usual bucket and value bounds."""
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import natural
+    from oracle import nnedi3_np
+
+    _need_gpu()
+    h, w = 150, 210
+    if name.startswith("nnedi3"):
+        hk = HookFile.parse(hook_path(name))
+        img = natural(h, w, seed=77)
+        ref, _ = nnedi3_np.nnedi3(img, hk.variant)
+        check_output(prescale(torch.from_numpy(img).cuda(), hk).cpu().numpy(), ref, None, f"{name} natural")
+        return
+    osz = None if ratio is None else (int(h * ratio[0]), int(w * ratio[1]))
+    # ravu (three passes): on IDENTICAL inputs every key obeys the 99.99 % rule here as everywhere (checked inside the
+    # helper: key 0 against the oracle, keys 1 / 2 against the oracle run on the device's own int11).  The end-to-end count
+    # of differing keys also contains the cascade of last-bit int11 differences through ill-conditioned keys, and smooth
+    # 1/f planes have many of those: measured 2.2e-4 (ravu-r2-rgb) against < 1e-4 on the band-limited mixture.
+    _run_ravu_variant(name, 1, h, w, 0, out_hw=osz, cascade_tol=5e-4,
+                      planes=lambda v: natural(h, w, seed=77, c=v.channels).reshape(1, v.channels, h, w))
 
 
 # ---- size-independent properties at BASELINE sizes -------------------------------------------------

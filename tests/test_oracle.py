@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from mpv_prescalers_b200.hookfile import HookFile
-from mpv_prescalers_b200.synth import batch, pathological
+from mpv_prescalers_b200.synth import batch, natural, pathological
 from oracle import nnedi3_np, ravu_np
 from tests.conftest import hook_path
 
@@ -53,6 +53,20 @@ def test_oracle_bit_exact_vs_literal_shader(name, out_size):
     img = _img(x)
     kw = {"out_size": out_size} if out_size else {}
     ref, off, applied = run_hook(path, img, **kw)
+    r = ravu_np.run(img, v, out_size)
+    assert applied and np.array_equal(r.out, ref) and tuple(off) == tuple(r.offset)
+
+
+@pytest.mark.parametrize("name,out_size", [("ravu-lite-ar-r3.hook", None), ("ravu-r2.hook", None), ("ravu-zoom-ar-r2.hook", (70, 55))])
+def test_oracle_bit_exact_vs_literal_shader_on_a_natural_plane(name, out_size):
+    """The same pinning on a 1/f-spectrum plane: other buckets, other clamps than the synthetic mixture."""
+    from oracle.glsl_exec import run_hook
+
+    path = hook_path(name)
+    v = HookFile.parse(path).variant
+    img = natural(22, 30, seed=5)
+    assert img.dtype == np.float32 and 0.0 <= img.min() and img.max() <= 1.0 and np.array_equal(img, natural(22, 30, seed=5))
+    ref, off, applied = run_hook(path, img, **({"out_size": out_size} if out_size else {}))
     r = ravu_np.run(img, v, out_size)
     assert applied and np.array_equal(r.out, ref) and tuple(off) == tuple(r.offset)
 
