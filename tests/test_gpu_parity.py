@@ -546,6 +546,51 @@ def test_pathological_planes(name):
             assert np.mean(d > 1e-3) <= 0.02 and psnr(np.nan_to_num(out), np.nan_to_num(ref)) >= 40.0, f"{name} {pname}"
 
 
+def _random_sizes(seed, count, hmax, wmax):
+    """Seeded (h, w) pairs biased towards tile seams: multiples of 32 / 64 and of 4 (the 16-byte TMA row rule), +-1."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        h, w = int(rng.integers(1, hmax + 1)), int(rng.integers(1, wmax + 1))
+        if rng.random() < 0.6:
+            w = max(1, int(rng.choice([32, 64, 96, 128, 192, 256])) + int(rng.integers(-1, 2)))
+        if rng.random() < 0.4:
+            h = max(1, int(rng.choice([4, 8, 16, 32, 64, 128])) + int(rng.integers(-1, 2)))
+        if rng.random() < 0.5:
+            w = max(4, w // 4 * 4)          # TMA-eligible pitch
+        out.append((h, w))
+    return out
+
+
+@pytest.mark.parametrize("name,seed", [("ravu-lite-ar-r2.hook", 1), ("ravu-lite-r4.hook", 2), ("ravu-r2.hook", 3), ("ravu-r4-yuv.hook", 4),
+                                       ("compute/ravu-3x-r4.hook", 5), ("ravu-zoom-r2.hook", 6), ("ravu-zoom-ar-r2.hook", 7)])
+def test_random_plane_sizes_ravu(name, seed):
+    """Seeded random plane sizes around the tile seams of every RAVU kernel (TMA and plain staging), two frames each, full
+    bucket + value comparison with the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    for h, w in _random_sizes(seed, 12, 140, 260):
+        out_hw = None
+        if "zoom" in name:
+            out_hw = (int(h * rng.uniform(1.0, 3.2)) + 1, int(w * rng.uniform(1.0, 3.2)) + 1)
+        _run_ravu_variant(name, n=2, h=h, w=w, config=40 + seed, out_hw=out_hw)
+
+
+@pytest.mark.parametrize("name,seed", [("nnedi3-nns16-win8x6.hook", 11), ("nnedi3-nns64-win8x4.hook", 12), ("nnedi3-nns128-win8x6.hook", 13)])
+def test_random_plane_sizes_nnedi3(name, seed):
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from oracle import nnedi3_np
+
+    _need_gpu()
+    hk = HookFile.parse(hook_path(name))
+    for h, w in _random_sizes(seed, 10, 70, 200):
+        x = batch(2, 1, h, w, config=50 + seed)
+        out = prescale(torch.from_numpy(x).cuda(), hk).cpu().numpy()
+        for f in range(2):
+            ref, _ = nnedi3_np.nnedi3(x[f, 0], hk.variant)
+            check_output(out[f, 0], ref, None, f"{name} {h}x{w} frame {f}")
+
+
 NATURAL_CASES = [("ravu-lite-ar-r3.hook", None), ("ravu-lite-r4.hook", None), ("ravu-r3.hook", None), ("ravu-r2-rgb.hook", None),
                  ("compute/ravu-3x-r3.hook", None), ("ravu-zoom-r3.hook", (3, 3)), ("ravu-zoom-ar-r2.hook", (2.37, 2.11)),
                  ("nnedi3-nns64-win8x6.hook", None), ("nnedi3-nns16-win8x4.hook", None)]
