@@ -42,9 +42,14 @@ for hook, shape, osz in (("ravu-lite-ar-r3.hook", (2, 120, 200), None), ("ravu-r
     torch.cuda.synchronize()
     print(hook, "grid limit 2", tuple(out.shape), "ok")
 _native.lib().mpvp_debug_set_grid_limit(0)
-out = resample(torch.rand(2, 50, 70, device="cuda"), (75, 101), (-0.5, -0.5), "lanczos")
+for shape, osz, kern in (((2, 50, 70), (75, 101), "lanczos"), ((2, 200, 300), (200, 300), "lanczos"),      # edge tiles only / interior tiles
+                         ((1, 260, 280), (150, 170), "catmull_rom"), ((1, 130, 140), (260, 280), "bilinear")):
+    out = resample(torch.rand(*shape, device="cuda"), osz, (-0.5, -0.5), kern)
+    torch.cuda.synchronize()
+    print("resample", kern, tuple(out.shape), "ok")
+out = resample(torch.randint(0, 256, (2, 200, 300), dtype=torch.uint8, device="cuda"), (200, 300), (-0.5, -0.5), "spline36")
 torch.cuda.synchronize()
-print("resample", tuple(out.shape), "ok")
+print("resample uint8", tuple(out.shape), "ok")
 u8 = torch.randint(0, 256, (2, 48, 80), dtype=torch.uint8, device="cuda")
 for hook in ("ravu-lite-ar-r3.hook", "ravu-r3.hook", "nnedi3-nns32-win8x4.hook"):
     out = prescale(u8, hook)
