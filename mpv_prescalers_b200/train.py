@@ -14,6 +14,13 @@ centre is the source pixel itself, the other eight are filters ``W_0..W_7`` in o
 (``res0`` / ``res1``), with ``W_{7-p} = reverse(W_p)`` (``compute/ravu-3x-r2.hook:84-114``: the mirrored tap reads
 ``w1.wzyx`` into ``res0`` and ``w0.wzyx`` into ``res1``), so four weight vectors are solved per bucket.
 
+The three-pass RAVU (``ravu-rN.hook``) applies ONE LUT three times: to the source lattice (pass 1: the pixel at
+(x+1/2, y+1/2)) and twice to the 45-degree lattice of source pixels and pass-1 results (passes 2 / 3: (x+1/2, y) and
+(x, y+1/2); ``ravu-r2.hook:15-338``), with one weight per mirrored tap pair (``res += (s_k + s_{N-1-k}) * w_k``).
+:func:`train_ravu_chain` pools the windows of all three passes per bucket; the windows and buckets of passes 2 / 3 are
+those the hook itself produces with its current LUT (they contain its own pass-1 results, exactly as at run time), so one
+call is one step of a fixed-point iteration -- ``rounds`` > 1 re-runs the hook with the LUT of the previous round.
+
 Everything runs on the GPU: the buckets come from the same CUDA key kernel the hook uses at run time
 (``prescale(..., return_buckets=True)``), the normal equations are accumulated per bucket in float64, and the result is
 written back as a complete ``.hook`` file (the original GLSL, a new payload line), which ``prescale()`` accepts like a
@@ -32,7 +39,7 @@ import torch
 
 from .hookfile import HookError, HookFile
 
-__all__ = ["train_ravu", "train_ravu_lite", "write_hook_with_lut", "lut_to_hex"]
+__all__ = ["train_ravu", "train_ravu_lite", "train_ravu_chain", "write_hook_with_lut", "lut_to_hex"]
 
 
 def _windows(lr: torch.Tensor, radius: int) -> torch.Tensor:
@@ -135,6 +142,104 @@ def train_ravu_lite(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: f
     if hook.variant.family != "ravu-lite":
         raise HookError("train_ravu_lite() trains the RAVU-Lite family")
     return train_ravu(hook, lr, hr, ridge, min_samples, exclude_clipped)
+
+
+def _chain_taps(r: int):
+    """Tap positions of the three passes on the 2x OUTPUT grid, relative to (2x, 2y): a list per pass of ``(dx2, dy2)`` in
+    tap order t = i*n + j.  Pass 1 taps HOOKED at (x + i - (r-1), y + j - (r-1)); passes 2 / 3 tap the lattice point at twice
+    the real position ``(tx2 - (2r-1) + i + j, ty2 - i + j)`` -- even = HOOKED, odd = the saved pass-1 texture
+    (``ravu-r2.hook:137-180``: the 45-degree lattice, i along (1/2, -1/2), j along (1/2, 1/2))."""
+    n = 2 * r
+    p1 = [(2 * (t // n - (r - 1)), 2 * (t % n - (r - 1))) for t in range(n * n)]
+    out = [p1]
+    for tx2, ty2 in ((1, 0), (0, 1)):
+        out.append([(tx2 - (2 * r - 1) + t // n + t % n, ty2 - t // n + t % n) for t in range(n * n)])
+    return out
+
+
+def _gather_lattice(out2: torch.Tensor, dx2: int, dy2: int) -> torch.Tensor:
+    """Sample of every source pixel (x, y) at output-grid offset (dx2, dy2) from (2x, 2y), clamp-to-edge applied per texture
+    like the host does: even offsets address HOOKED, odd ones the half-resolution pass-1 texture."""
+    h2, w2 = out2.shape
+    h, w = h2 // 2, w2 // 2
+    par = dx2 & 1                                                 # dy2 has the same parity by construction
+    ys = torch.arange(h, device=out2.device) + (dy2 - par) // 2
+    xs = torch.arange(w, device=out2.device) + (dx2 - par) // 2
+    ys = ys.clamp_(0, h - 1) * 2 + par
+    xs = xs.clamp_(0, w - 1) * 2 + par
+    return out2[ys[:, None], xs[None, :]]
+
+
+def train_ravu_chain(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: float = 1e-9, min_samples: Optional[int] = None,
+                     exclude_clipped: bool = True, rounds: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+    """Least-squares LUT of a three-pass luma RAVU hook (``ravu-rN.hook``) from training pairs.
+
+    lr ``[F, H, W]``, hr ``[F, 2H, 2W]`` float32 CUDA planes; hr is aligned like the hook's output: hr[2y, 2x] is the
+    source pixel, hr[2y+1, 2x+1] / hr[2y, 2x+1] / hr[2y+1, 2x] the targets of passes 1 / 2 / 3 (``ravu-r2.hook:327-338``).
+    Returns ``(lut [rows, LW, 4] float32, samples_per_bucket [rows])`` (all three passes pooled)."""
+    import os
+    import tempfile
+
+    from .api import prescale
+
+    v = hook.variant
+    if v.family != "ravu" or v.plane != "luma":
+        raise HookError("train_ravu_chain() trains the three-pass luma RAVU hooks (ravu-rN.hook)")
+    if lr.device.type != "cuda" or hr.device.type != "cuda":
+        raise ValueError("training planes must be CUDA tensors")
+    f, h, w = lr.shape
+    if tuple(hr.shape) != (f, 2 * h, 2 * w):
+        raise ValueError(f"hr must be {(f, 2 * h, 2 * w)}, got {tuple(hr.shape)}")
+    r = v.radius
+    N = (2 * r) ** 2
+    half = N // 2
+    rows = int(v.lut.height)
+    taps = _chain_taps(r)
+    tgt = ((1, 1), (1, 0), (0, 1))                                 # (dx, dy) of the pass's target inside the 2x2 cell
+    dev = lr.device
+    cur = hook
+    lut = np.asarray(v.lut.data, dtype=np.float32).copy()
+    count_h = np.zeros(rows, np.int64)
+    tmpdir = tempfile.mkdtemp(prefix="mpvp_train_") if rounds > 1 else None
+    for rnd in range(max(1, int(rounds))):
+        A = torch.zeros((rows, half, half), dtype=torch.float64, device=dev)
+        B = torch.zeros((rows, half), dtype=torch.float64, device=dev)
+        count = torch.zeros(rows, dtype=torch.int64, device=dev)
+        out, buckets = prescale(lr, cur, return_buckets=True)      # [F, 2H, 2W], [F, 3, H, W]: the hook's own lattice and keys
+        for k in range(f):
+            for ps in range(3):
+                cols = [_gather_lattice(out[k], dx2, dy2).reshape(-1) for dx2, dy2 in taps[ps]]
+                X = torch.stack([cols[t] + cols[N - 1 - t] for t in range(half)], dim=1)     # one weight per mirrored pair
+                y = hr[k][tgt[ps][1]::2, tgt[ps][0]::2].reshape(-1)
+                b = buckets[k, ps].reshape(-1).long()
+                if exclude_clipped:
+                    keep = (y > 0.0) & (y < 1.0)
+                    X, y, b = X[keep], y[keep], b[keep]
+                order = torch.argsort(b)
+                X, y, b = X[order], y[order], b[order]
+                cnt = torch.bincount(b, minlength=rows)
+                count += cnt
+                starts = torch.cumsum(cnt, 0) - cnt
+                for row in torch.nonzero(cnt).reshape(-1).tolist():
+                    s0, m = int(starts[row]), int(cnt[row])
+                    xb, yb = X[s0:s0 + m].double(), y[s0:s0 + m].double()
+                    A[row] += xb.T @ xb
+                    B[row] += xb.T @ yb
+        need = (8 * half) if min_samples is None else int(min_samples)
+        count_h = count.cpu().numpy()
+        eye = torch.eye(half, dtype=torch.float64, device=dev)
+        flat = lut.reshape(rows, -1).copy()                        # weight k of a row sits at texel k // 4, component k % 4
+        for row in range(rows):
+            if count_h[row] < need:
+                continue
+            lam = ridge * float(torch.diagonal(A[row]).mean())
+            flat[row, :half] = torch.linalg.solve(A[row] + lam * eye, B[row]).cpu().numpy()
+        lut = flat.reshape(lut.shape).astype(np.float32)
+        if rnd + 1 < rounds:
+            path = os.path.join(tmpdir, f"round{rnd}.hook")
+            write_hook_with_lut(hook, lut, path)
+            cur = HookFile.parse(path)
+    return lut, count_h
 
 
 def lut_to_hex(lut: np.ndarray) -> str:

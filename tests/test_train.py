@@ -58,12 +58,72 @@ def test_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
     assert psnr(a.cpu().numpy(), b.cpu().numpy()) >= 60.0
 
 
+@pytest.mark.parametrize("r", [2, 3, 4])
+def test_chain_lattice_reproduces_the_three_passes(r):
+    """The trainer's own tap geometry of ravu's passes (source lattice, then the 45-degree lattice of source pixels and pass-1
+    results, clamp-to-edge per texture), applied with the shipped LUT to the oracle's output plane, gives the oracle's
+    int11 / int10 / int01 planes back bit for bit."""
+    torch = pytest.importorskip("torch")
+    from mpv_prescalers_b200 import HookFile
+    from mpv_prescalers_b200.synth import batch
+    from mpv_prescalers_b200.train import _chain_taps, _gather_lattice
+    from oracle import ravu_np
+
+    v = HookFile.parse(hook_path(f"ravu-r{r}.hook")).variant
+    x = batch(1, 1, 18, 23, config=93)[0, 0]
+    res, inter = ravu_np.ravu(x, v, return_intermediates=True)
+    out = torch.from_numpy(res.out)
+    N = (2 * r) ** 2
+    lut = ravu_np.lut_array(v.lut, "fp16")
+    for ps, name in enumerate(("ravu_int11", "ravu_int10", "ravu_int01")):
+        cols = [_gather_lattice(out, dx2, dy2).numpy() for dx2, dy2 in _chain_taps(r)[ps]]
+        w_all = lut[res.keys[ps].row].reshape(res.keys[ps].row.shape + (-1,))
+        acc = np.zeros_like(cols[0])
+        for k in range(N // 2):
+            acc = acc + (cols[k] + cols[N - 1 - k]) * w_all[..., k]
+        assert np.array_equal(np.clip(acc, 0, 1), inter[name][..., 0]), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ravu-r2.hook", "ravu-r3.hook"])
+def test_chain_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
+    """Targets made by the shipped three-pass hook are, per bucket, a linear function of the pooled windows of its three
+    passes: one round of least squares is the fixed point and returns the shipped LUT; a second round stays there."""
+    import torch
+
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from mpv_prescalers_b200.train import train_ravu_chain, write_hook_with_lut
+    from tests.parity import psnr
+
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device")
+    hk = HookFile.parse(hook_path(name))
+    rng = np.random.default_rng(6)
+    x = batch(6, 1, 300, 400, config=94)[:, 0]
+    x = np.clip(0.2 + 0.6 * x + rng.normal(0, 0.04, x.shape), 0.02, 0.98).astype(np.float32)
+    lr = torch.from_numpy(x).cuda()
+    hr = prescale(lr, hk)
+    half = (2 * hk.variant.radius) ** 2 // 2
+    ref = np.asarray(hk.variant.lut.data, np.float32).astype(np.float16).astype(np.float32).reshape(hk.variant.lut.height, -1)[:, :half]
+    for rounds in (1, 2):
+        lut, count = train_ravu_chain(hk, lr, hr, rounds=rounds)
+        got = lut.reshape(lut.shape[0], -1)[:, :half]
+        well = count >= 5000
+        assert well.sum() >= 20, f"only {well.sum()} well-populated buckets"
+        assert np.abs(got[well] - ref[well]).max() <= 3e-3, f"rounds={rounds}: recovered LUT differs by {np.abs(got[well] - ref[well]).max():.2e}"
+    out = tmp_path / "retrained.hook"
+    write_hook_with_lut(hk, lut, str(out))
+    fresh = torch.from_numpy(np.clip(0.2 + 0.6 * batch(1, 1, 200, 300, config=95)[:, 0], 0, 1).astype(np.float32)).cuda()
+    assert psnr(prescale(fresh, hk).cpu().numpy(), prescale(fresh, str(out)).cpu().numpy()) >= 55.0
+
+
 def test_trainer_refuses_families_it_does_not_cover():
     pytest.importorskip("torch")
     import torch
 
     from mpv_prescalers_b200 import HookError, HookFile
-    from mpv_prescalers_b200.train import train_ravu, train_ravu_lite
+    from mpv_prescalers_b200.train import train_ravu, train_ravu_chain, train_ravu_lite
 
     z = torch.zeros((1, 4, 4))
     for name in ("ravu-r2.hook", "ravu-zoom-r2.hook", "compute/ravu-3x-r2-rgb.hook"):
@@ -71,3 +131,6 @@ def test_trainer_refuses_families_it_does_not_cover():
             train_ravu(HookFile.parse(hook_path(name)), z, z)
     with pytest.raises(HookError, match="RAVU-Lite"):
         train_ravu_lite(HookFile.parse(hook_path("compute/ravu-3x-r2.hook")), z, z)
+    for name in ("ravu-lite-r2.hook", "ravu-r2-rgb.hook"):
+        with pytest.raises(HookError, match="three-pass luma"):
+            train_ravu_chain(HookFile.parse(hook_path(name)), z, z)
