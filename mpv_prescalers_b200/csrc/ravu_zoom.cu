@@ -410,7 +410,11 @@ int launch_zoom_general(const ZoomArgs& a, int device, cudaStream_t stream, bool
 // =====================================================================================================================
 // PHASE path
 // =====================================================================================================================
-constexpr int kPTW = 64, kPTH = 16;   // member tile: 64 x 16 output pixels of one class pair
+#ifndef MPVP_X_ZOOM_SPT
+#define MPVP_X_ZOOM_SPT 2   // strips per thread and tile: member tiles of 64 x 32, the per-tile set-up amortised over 8 pixels (1 / 2 / 4: 0.933 / 0.873 / 0.882 ms, zoom-r3 x8)
+#endif
+constexpr int kSPT = MPVP_X_ZOOM_SPT;
+constexpr int kPTW = 64, kPTH = 16 * kSPT;   // member tile: 64 x 16 (32) output pixels of one class pair
 constexpr int kMaxClasses = 8;                    // per axis
 constexpr int kMaxStep = 3;                       // base-texel distance of neighbouring class members
 constexpr float kClusterGap = 2.5e-4f;            // sub-pixel phases closer than this belong to one class ...
@@ -579,7 +583,7 @@ __device__ __forceinline__ void store_px_wb(void* __restrict__ p, int64_t off, f
 #define MPVP_X_ZOOM_STRIP 4
 #endif
 constexpr int kStrip = MPVP_X_ZOOM_STRIP;
-constexpr int kPNT2 = kPTW * kPTH / kStrip;
+constexpr int kPNT2 = kPTW * kPTH / (kStrip * kSPT);
 #ifndef MPVP_X_ZOOM_MINB
 #define MPVP_X_ZOOM_MINB 3   // resident CTAs per SM of the luma phase kernel (4 = 64 registers: measured)
 #endif
@@ -708,7 +712,9 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
     __syncthreads();
 
     const int lx = tid & (kPTW - 1);
-    const int ly0 = (tid / kPTW) * STRIP;            // this thread's member rows: ly0 .. ly0 + STRIP - 1
+#pragma unroll 1
+    for (int sp = 0; sp < kSPT; ++sp) {
+    const int ly0 = (tid / kPTW + sp * (kPNT / kPTW)) * STRIP;   // this thread's member rows: ly0 .. ly0 + STRIP - 1
     if (lx >= nmx || ly0 >= nmy) continue;
     const int cnt = min(STRIP, nmy - ly0);
     const int ox = s_mxo[lx], bx = s_mxb[lx];
@@ -824,6 +830,7 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
         pixel(k, rows[k], [&](int c, int i, int j) { return kb[c * PLANE + j * SW + i]; });
       }
     }
+    }   // strips of this thread
   }
 }
 
