@@ -368,6 +368,31 @@ class Runner:
         return res
 
 
+def bind_to_gpu_cpus(torch, local_rank):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU BEFORE any pinned host buffer is
+    allocated (first touch places the pages on that NUMA node), so the end-to-end copies of eight ranks do not all cross
+    the socket interconnect.  Returns the number of CPUs bound to, or None when the GPU is local to every CPU the process
+    may use (single-socket boxes, the 1-GPU lease) or NVML is not available."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus_id = f"{getattr(pr, 'pci_domain_id', 0):08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        words = (max(os.sched_getaffinity(0)) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        local &= cur
+        if local and local != cur:
+            os.sched_setaffinity(0, local)
+            return len(local)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,9 +432,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    host_cpus = None
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("MPVP_BENCH_BIND", "1") != "0":        # A/B switch for the NUMA binding
+            host_cpus = bind_to_gpu_cpus(torch, local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     warm = max(args.warmup, 3)
@@ -469,6 +497,8 @@ def main():
             "data": "synthetic", "config": config_of(wl, nf, world, args.io), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if e2e is not None and host_cpus is not None:
+            e2e["host_cpus_per_rank"] = host_cpus        # ranks are bound to the CPUs local to their GPU (NUMA)
         if e2e_u8 is not None:
             line["e2e_u8_planes"] = e2e_u8
         if secondary:
