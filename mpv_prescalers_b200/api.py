@@ -60,6 +60,19 @@ def plan(hook: HookFile, in_hw: Tuple[int, int], output_size: Optional[Tuple[int
         oh, ow = h * v.scale, w * v.scale
     else:
         oh, ow = int(output_size[0]), int(output_size[1])
+    # a player asks the same question for every frame: the answer is kept on the (immutable) parsed file
+    cache = hook.__dict__.setdefault("_plan_cache", {})
+    ckey = (h, w, oh, ow, bool(is_yuv))
+    hit = cache.get(ckey)
+    if hit is not None:
+        return hit
+    pl = _plan_uncached(hook, v, h, w, oh, ow, is_yuv)
+    if len(cache) < 64:
+        cache[ckey] = pl
+    return pl
+
+
+def _plan_uncached(hook: HookFile, v: Variant, h: int, w: int, oh: int, ow: int, is_yuv: bool) -> Plan:
     env = {"HOOKED": (w, h), "OUTPUT": (ow, oh), "LUMA": (w if is_yuv else 0, h if is_yuv else 0), "NATIVE": (w, h), "MAIN": (w, h)}
     saved: Dict[str, Tuple[int, int]] = {}
     fired: List[str] = []
