@@ -521,13 +521,26 @@ __global__ void __launch_bounds__(kThreads, 1) nnedi3_tc_kernel(const __grid_con
 #endif
       constexpr int NB = CN / 32;
       constexpr bool EARLY = MPVP_X_NN_EARLY && EPI == 3 && NB >= 2;
+#ifndef MPVP_X_NN_ARV
+#define MPVP_X_NN_ARV 0   // chunk hand-over by mbarrier: the three non-issuing warps arrive and go on, only the issuing warp waits
+#endif
       auto accumulator_free = [&]() {
         if (c + 1 < NCH) {
           tc_fence_before();
+          if constexpr (MPVP_X_NN_ARV && !XT && !DB) {
+            if ((lt & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(free_bar) : "memory");
+            if (lt == 0) {
+              mbar_wait(free_bar, free_par & 1u);
+              tc_fence_after();
+              issue_chunk(c + 1, 0, aslot);
+            }
+            free_par ^= 1u;
+          } else {
           wg_barrier(wg);
           if (lt == 0) {
             tc_fence_after();
             issue_chunk(c + 1, 0, aslot);
+          }
           }
         } else if (XT && more) {
           // last block of the tile: the accumulator is free and (same barrier) the next tile's A operand is complete
