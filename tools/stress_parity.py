@@ -37,13 +37,19 @@ def main():
                 ratios = [(2.0, 2.0), (3.0, 3.0), (1.5, 1.5), (rng.uniform(1.0, 3.5), rng.uniform(1.0, 3.5))]
                 ry, rx = ratios[int(rng.integers(len(ratios)))]
                 out_hw = (max(h + 1, int(round(h * ry))), max(w + 1, int(round(w * rx))))     # the hook only fires when both axes grow
+            in_bits = None
+            if "zoom" not in name and rng.random() < 0.3:
+                in_bits = int(rng.choice([8, 10, 16]))           # UNORM integer planes in, float32 out
+            cap = int(rng.integers(1, 4)) if rng.random() < 0.3 else 0   # persistent grid capped to 1..3 CTAs: many tiles per CTA
             try:
+              with T.grid_limit(cap):
                 # cascade_tol: the end-to-end count of differing ravu keys (last-bit int11 differences amplified by
                 # ill-conditioned keys of passes 2 / 3) is a property of the algorithm, reported but not a parity failure;
                 # the comparison on identical inputs inside the helper keeps its 99.99 % / boundary-only rule
-                T._run_ravu_variant(name, n=n, h=h, w=w, config=int(rng.integers(100, 900)), out_hw=out_hw, cascade_tol=2e-3)
+                T._run_ravu_variant(name, n=n, h=h, w=w, config=int(rng.integers(100, 900)), out_hw=out_hw, cascade_tol=2e-3,
+                                    in_bits=in_bits)
             except Exception as e:  # keep going: the point is the list of failures
-                fails.append((name, n, h, w, out_hw, f"{type(e).__name__}: {str(e)[:200]}"))
+                fails.append((name, n, h, w, out_hw, in_bits, cap, f"{type(e).__name__}: {str(e)[:200]}"))
             runs += 1
     from mpv_prescalers_b200 import HookFile, prescale
     from mpv_prescalers_b200.synth import batch
@@ -54,8 +60,10 @@ def main():
         for h, w in T._random_sizes(int(rng.integers(1 << 30)), max(2, per // 2), 90, 220):
             n = int(rng.integers(1, 3))
             x = batch(n, 1, h, w, config=int(rng.integers(100, 900)))
+            cap = int(rng.integers(1, 4)) if rng.random() < 0.3 else 0
             try:
-                out = prescale(torch.from_numpy(x).cuda(), hk).cpu().numpy()
+                with T.grid_limit(cap):
+                    out = prescale(torch.from_numpy(x).cuda(), hk).cpu().numpy()
                 for f in range(n):
                     ref, _ = nnedi3_np.nnedi3(x[f, 0], hk.variant)
                     check_output(out[f, 0], ref, None, f"{name} {h}x{w}")
