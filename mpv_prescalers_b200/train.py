@@ -21,6 +21,14 @@ The three-pass RAVU (``ravu-rN.hook``) applies ONE LUT three times: to the sourc
 those the hook itself produces with its current LUT (they contain its own pass-1 results, exactly as at run time), so one
 call is one step of a fixed-point iteration -- ``rounds`` > 1 re-runs the hook with the LUT of the previous round.
 
+RAVU-Zoom (``ravu-zoom-rN.hook``) stores, per bucket, a 9 x 9 grid of filters over the sub-pixel phase and lets the sampler
+blend the four nodes around (8 sx, 8 sy) (``LUTPOS``, ``ravu-zoom-r2.hook:23,112-131``); the first half of the taps is
+weighted at phase (sx, sy), the mirrored half at (1 - sx, 1 - sy).  The output is still linear in the node filters, so
+:func:`train_ravu_zoom` solves one least-squares problem per bucket in the 81 * N/2 node weights, from training pairs at
+several scale factors (the phases must cover the grid), regularised towards the hook's own LUT so that nodes no sample
+reaches keep their values.  The anti-ringing LUTs (``ravu_zoom_lutN_ar``) are not trained: their objective is stated
+nowhere in the reference.
+
 Everything runs on the GPU: the buckets come from the same CUDA key kernel the hook uses at run time
 (``prescale(..., return_buckets=True)``), the normal equations are accumulated per bucket in float64, and the result is
 written back as a complete ``.hook`` file (the original GLSL, a new payload line), which ``prescale()`` accepts like a
@@ -39,7 +47,7 @@ import torch
 
 from .hookfile import HookError, HookFile
 
-__all__ = ["train_ravu", "train_ravu_lite", "train_ravu_chain", "write_hook_with_lut", "lut_to_hex"]
+__all__ = ["train_ravu", "train_ravu_lite", "train_ravu_chain", "train_ravu_zoom", "write_hook_with_lut", "lut_to_hex"]
 
 
 def _windows(lr: torch.Tensor, radius: int) -> torch.Tensor:
@@ -240,6 +248,119 @@ def train_ravu_chain(hook: HookFile, lr: torch.Tensor, hr: torch.Tensor, ridge: 
             write_hook_with_lut(hook, lut, path)
             cur = HookFile.parse(path)
     return lut, count_h
+
+
+def _zoom_axis(in_size: int, out_size: int, dev):
+    """Base texel, node index and node blend weight of every output coordinate (``pos = (o + 1/2) / O * I`` in float32 like
+    the shader; node coordinate 8 * sub)."""
+    o = torch.arange(out_size, dtype=torch.float32, device=dev)
+    pos = ((o + 0.5) / float(out_size)) * float(in_size)
+    t = pos - 0.5
+    sub = t - torch.floor(t)
+    base = torch.floor(pos - sub).long()
+    return base, sub.double()
+
+
+def _node_basis(t: torch.Tensor):
+    """(i0, i1, w0, w1): the two LUT nodes around 8 t and their blend weights (t in [0, 1], node 8 reached only at t = 1)."""
+    u = (8.0 * t).clamp(0.0, 8.0)
+    i0 = torch.floor(u).clamp(max=8.0)
+    f = u - i0
+    i0 = i0.long()
+    return i0, (i0 + 1).clamp(max=8), 1.0 - f, f
+
+
+def train_ravu_zoom(hook: HookFile, pairs, ridge: float = 1e-6, min_samples: Optional[int] = None,
+                    exclude_clipped: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Least-squares LUT of a luma RAVU-Zoom hook (``ravu-zoom-rN.hook``, not the -ar files).
+
+    pairs  a list of ``(lr [F, H, W], hr [F, OH, OW])`` float32 CUDA planes, ONE scale factor per pair and several pairs:
+           hr[oy, ox] is the true value at the position the hook computes for output pixel (ox, oy) (centre-aligned,
+           ``pos = (o + 1/2) * I / O``);
+    ridge  pulls the solution towards the hook's own LUT (relative to the mean diagonal of the normal matrix): nodes that
+           no training phase reaches keep their values.
+
+    Returns ``(lut [288 * 9, B * 9, 4] float32, samples_per_bucket [288])``."""
+    from .api import prescale
+
+    v = hook.variant
+    if v.family != "ravu-zoom" or v.plane != "luma" or v.ar:
+        raise HookError("train_ravu_zoom() trains the luma RAVU-Zoom hooks without anti-ringing (ravu-zoom-rN.hook)")
+    r = v.radius
+    n = 2 * r
+    N, H2 = n * n, n * n // 2
+    B = (H2 + 3) // 4
+    rows = int(v.lut.height) // 9
+    D = 81 * H2
+    lut_old = np.asarray(v.lut.data, dtype=np.float32)                       # [rows * 9, B * 9, 4]
+    if lut_old.shape != (rows * 9, B * 9, 4):
+        raise HookError(f"unexpected LUT geometry {lut_old.shape}")
+    # node-major weight vector of a bucket: W[ny, nx, k], k = blk * 4 + comp
+    w_old = lut_old.reshape(rows, 9, B, 9, 4).transpose(0, 1, 3, 2, 4).reshape(rows, 9, 9, B * 4)[..., :H2]
+    dev = pairs[0][0].device
+    W0 = torch.from_numpy(np.ascontiguousarray(w_old)).to(dev).double().reshape(rows, D)
+    A = torch.zeros((rows, D, D), dtype=torch.float64, device=dev)
+    G = torch.zeros((rows, D), dtype=torch.float64, device=dev)               # X^T (y - X w_old)
+    count = torch.zeros(rows, dtype=torch.int64, device=dev)
+    for lr, hr in pairs:
+        if lr.device.type != "cuda" or hr.device.type != "cuda":
+            raise ValueError("training planes must be CUDA tensors")
+        f, h, w = lr.shape
+        oh, ow = int(hr.shape[1]), int(hr.shape[2])
+        if hr.shape[0] != f or oh <= h or ow <= w:
+            raise ValueError("every pair needs hr planes larger than its lr planes on both axes")
+        _, buckets = prescale(lr, hook, output_size=(oh, ow), return_buckets=True)      # [F, OH, OW]
+        bx, sx = _zoom_axis(w, ow, dev)
+        by, sy = _zoom_axis(h, oh, dev)
+        nodes = {}
+        for tag, tx, ty in (("d", sx, sy), ("m", 1.0 - sx, 1.0 - sy)):
+            x0, x1, wx0, wx1 = _node_basis(tx)
+            y0, y1, wy0, wy1 = _node_basis(ty)
+            nodes[tag] = [((ya[:, None] * 9 + xa[None, :]).reshape(-1), (wya[:, None] * wxa[None, :]).reshape(-1))
+                          for ya, wya in ((y0, wy0), (y1, wy1)) for xa, wxa in ((x0, wx0), (x1, wx1))]
+        for k in range(f):
+            src = lr[k]
+            taps = []
+            for t in range(N):                                               # t = i * n + j, i <-> dx, j <-> dy
+                yy = (by + (t % n - (r - 1))).clamp(0, h - 1)
+                xx = (bx + (t // n - (r - 1))).clamp(0, w - 1)
+                taps.append(src[yy[:, None], xx[None, :]].reshape(-1))
+            S = torch.stack(taps, dim=1).double()                            # [P, N]
+            Sd, Sm = S[:, :H2], S[:, torch.arange(N - 1, N - 1 - H2, -1, device=dev)]
+            y = hr[k].reshape(-1).double()
+            b = buckets[k].reshape(-1).long()
+            keep = ((y > 0.0) & (y < 1.0)) if exclude_clipped else torch.ones_like(b, dtype=torch.bool)
+            order = torch.argsort(b[keep])
+            sel = torch.nonzero(keep).reshape(-1)[order]
+            bs = b[sel]
+            cnt = torch.bincount(bs, minlength=rows)
+            count += cnt
+            starts = torch.cumsum(cnt, 0) - cnt
+            for row in torch.nonzero(cnt).reshape(-1).tolist():
+                ids = sel[int(starts[row]):int(starts[row]) + int(cnt[row])]
+                m = ids.numel()
+                X = torch.zeros((m, 81, H2), dtype=torch.float64, device=dev)
+                ar = torch.arange(m, device=dev)
+                for tag, Sv in (("d", Sd), ("m", Sm)):
+                    for idx, wgt in nodes[tag]:
+                        X[ar, idx[ids]] += wgt[ids][:, None] * Sv[ids]
+                X = X.reshape(m, D)
+                A[row] += X.T @ X
+                G[row] += X.T @ (y[ids] - X @ W0[row])
+    need = (4 * H2) if min_samples is None else int(min_samples)
+    count_h = count.cpu().numpy()
+    eye = torch.eye(D, dtype=torch.float64, device=dev)
+    Wn = W0.clone()
+    for row in range(rows):
+        if count_h[row] < need:
+            continue
+        lam = ridge * float(torch.diagonal(A[row]).mean())
+        Wn[row] = W0[row] + torch.linalg.solve(A[row] + lam * eye, G[row])
+    full = np.zeros((rows, 9, 9, B * 4), np.float32)
+    full[..., :H2] = Wn.reshape(rows, 9, 9, H2).cpu().numpy()
+    full[..., H2:] = lut_old.reshape(rows, 9, B, 9, 4).transpose(0, 1, 3, 2, 4).reshape(rows, 9, 9, B * 4)[..., H2:]
+    lut = full.reshape(rows, 9, 9, B, 4).transpose(0, 1, 3, 2, 4).reshape(rows * 9, B * 9, 4)
+    return np.ascontiguousarray(lut, dtype=np.float32), count_h
 
 
 def lut_to_hex(lut: np.ndarray) -> str:

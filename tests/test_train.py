@@ -118,12 +118,82 @@ def test_chain_trainer_recovers_the_lut_that_made_the_targets(name, tmp_path):
     assert psnr(prescale(fresh, hk).cpu().numpy(), prescale(fresh, str(out)).cpu().numpy()) >= 55.0
 
 
+def test_zoom_node_model_reproduces_the_oracle():
+    """The trainer's linear model of ravu-zoom -- node filters blended with (1 - f, f) around 8 * sub, first half of the taps
+    at (sx, sy), mirrored half at (1 - sx, 1 - sy) -- evaluated in float64 with the shipped LUT gives the oracle's output."""
+    torch = pytest.importorskip("torch")
+    from mpv_prescalers_b200 import HookFile
+    from mpv_prescalers_b200.synth import batch
+    from mpv_prescalers_b200.train import _node_basis, _zoom_axis
+    from oracle import ravu_np
+
+    v = HookFile.parse(hook_path("ravu-zoom-r2.hook")).variant
+    h, w, OH, OW = 26, 34, 61, 83
+    x = batch(1, 1, h, w, config=96)[0, 0]
+    res = ravu_np.ravu_zoom(x, v, (OW, OH))
+    r = v.radius
+    n = 2 * r
+    N, H2 = n * n, n * n // 2
+    B = (H2 + 3) // 4
+    lut = ravu_np.lut_array(v.lut, "fp16")
+    wn = lut.reshape(288, 9, B, 9, 4).transpose(0, 1, 3, 2, 4).reshape(288, 9, 9, B * 4)[..., :H2].astype(np.float64)
+    bx, sx = _zoom_axis(w, OW, "cpu")
+    by, sy = _zoom_axis(h, OH, "cpu")
+    src = torch.from_numpy(x)
+    S = np.stack([src[(by + (t % n - (r - 1))).clamp(0, h - 1)[:, None], (bx + (t // n - (r - 1))).clamp(0, w - 1)[None, :]].double().numpy()
+                  for t in range(N)], -1)
+    row = res.keys[0].row
+    out = np.zeros((OH, OW))
+    for tx, ty, sel in ((sx, sy, list(range(H2))), (1 - sx, 1 - sy, [N - 1 - k for k in range(H2)])):
+        x0, x1, wx0, wx1 = [a.numpy() for a in _node_basis(tx)]
+        y0, y1, wy0, wy1 = [a.numpy() for a in _node_basis(ty)]
+        for ya, wya in ((y0, wy0), (y1, wy1)):
+            for xa, wxa in ((x0, wx0), (x1, wx1)):
+                out += (wya[:, None] * wxa[None, :]) * np.sum(wn[row, ya[:, None], xa[None, :]] * S[..., sel], -1)
+    assert np.abs(np.clip(out, 0, 1) - res.out).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_zoom_trainer_recovers_the_lut_that_made_the_targets(tmp_path):
+    """Targets made by the shipped ravu-zoom-r2 LUT at three scale factors are linear in its 81 node filters per bucket; the
+    regularised least squares returns them (nodes of well-populated buckets), and the retrained file reproduces the
+    original on an unseen plane at a fourth scale factor."""
+    import torch
+
+    from mpv_prescalers_b200 import HookFile, prescale
+    from mpv_prescalers_b200.synth import batch
+    from mpv_prescalers_b200.train import train_ravu_zoom, write_hook_with_lut
+    from tests.parity import psnr
+
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device")
+    hk = HookFile.parse(hook_path("ravu-zoom-r2.hook"))
+    rng = np.random.default_rng(8)
+    pairs = []
+    for k, (ry, rx) in enumerate(((1.37, 1.61), (2.23, 1.93), (2.9, 3.1))):
+        x = batch(4, 1, 200, 260, config=97 + k)[:, 0]
+        x = np.clip(0.2 + 0.6 * x + rng.normal(0, 0.04, x.shape), 0.02, 0.98).astype(np.float32)
+        lr = torch.from_numpy(x).cuda()
+        pairs.append((lr, prescale(lr, hk, output_size=(int(200 * ry), int(260 * rx)))))
+    lut, count = train_ravu_zoom(hk, pairs)
+    ref = np.asarray(hk.variant.lut.data, np.float32).astype(np.float16).astype(np.float32)
+    well = np.repeat(count >= 30000, 9)                                       # the nine node rows of a well-populated bucket
+    assert well.sum() >= 9 * 10, f"only {well.sum() // 9} well-populated buckets"
+    err = np.abs(lut[well] - ref[well]).max()
+    assert err <= 5e-3, f"recovered node filters differ by {err:.2e}"
+    out = tmp_path / "retrained.hook"
+    write_hook_with_lut(hk, lut, str(out))
+    fresh = torch.from_numpy(np.clip(0.2 + 0.6 * batch(1, 1, 150, 210, config=99)[:, 0], 0, 1).astype(np.float32)).cuda()
+    a, b = prescale(fresh, hk, output_size=(330, 400)), prescale(fresh, str(out), output_size=(330, 400))
+    assert psnr(a.cpu().numpy(), b.cpu().numpy()) >= 55.0
+
+
 def test_trainer_refuses_families_it_does_not_cover():
     pytest.importorskip("torch")
     import torch
 
     from mpv_prescalers_b200 import HookError, HookFile
-    from mpv_prescalers_b200.train import train_ravu, train_ravu_chain, train_ravu_lite
+    from mpv_prescalers_b200.train import train_ravu, train_ravu_chain, train_ravu_lite, train_ravu_zoom
 
     z = torch.zeros((1, 4, 4))
     for name in ("ravu-r2.hook", "ravu-zoom-r2.hook", "compute/ravu-3x-r2-rgb.hook"):
@@ -134,3 +204,6 @@ def test_trainer_refuses_families_it_does_not_cover():
     for name in ("ravu-lite-r2.hook", "ravu-r2-rgb.hook"):
         with pytest.raises(HookError, match="three-pass luma"):
             train_ravu_chain(HookFile.parse(hook_path(name)), z, z)
+    for name in ("ravu-zoom-ar-r2.hook", "ravu-zoom-r2-yuv.hook", "ravu-r2.hook"):
+        with pytest.raises(HookError, match="without anti-ringing"):
+            train_ravu_zoom(HookFile.parse(hook_path(name)), [(z, z)])
