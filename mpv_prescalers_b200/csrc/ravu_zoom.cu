@@ -416,6 +416,7 @@ int launch_zoom_general(const ZoomArgs& a, int device, cudaStream_t stream, bool
 constexpr int kSPT = MPVP_X_ZOOM_SPT;
 constexpr int kPTW = 64, kPTH = 16 * kSPT;   // member tile: 64 x 16 (32) output pixels of one class pair
 constexpr int kMaxClasses = 8;                    // per axis
+constexpr int kMaxClassesExact = 32;              // per axis when the phases around a LUT node are kept apart (anti-ringing)
 constexpr int kMaxStep = 3;                       // base-texel distance of neighbouring class members
 constexpr float kClusterGap = 2.5e-4f;            // sub-pixel phases closer than this belong to one class ...
 constexpr float kMaxSpread = 2.6e-4f;             // ... whose total spread must stay below this (fp32 noise of `pos`)
@@ -560,7 +561,9 @@ template <int R, bool AR, bool MIX>
 struct PhaseGeom {
   static constexpr int TAPS = 4 * R * R;
   static constexpr int PL = TAPS * (AR ? 2 : 1);                       // floats per row of the global phase LUT
-  static constexpr int QUADS = MIX ? (16 + 2 * (TAPS - 4) + 15) / 16 : PL / 4;   // 16-byte units actually read per row
+  // anti-ringing rows in shared memory: TAPS float32 main weights + TAPS binary16 anti-ringing weights scaled by 2^13 (they are
+  // all >= 0 and <= 1.01, only RATIOS of sums weighted by them are used, so the scale cancels and small weights keep 11 bits)
+  static constexpr int QUADS = MIX ? (16 + 2 * (TAPS - 4) + 15) / 16 : (AR ? (TAPS * 4 + TAPS * 2 + 15) / 16 : PL / 4);   // 16-byte units read per row
   static constexpr int PITCH = (QUADS | 1) * 4;                        // floats per row in shared memory
 };
 
@@ -583,25 +586,34 @@ __device__ __forceinline__ void store_px_wb(void* __restrict__ p, int64_t off, f
 #define MPVP_X_ZOOM_STRIP 4
 #endif
 constexpr int kStrip = MPVP_X_ZOOM_STRIP;
+#ifndef MPVP_X_ZOOM_AR_MINB
+#define MPVP_X_ZOOM_AR_MINB 3   // resident CTAs per SM of the anti-ringing phase kernel (76 registers, no spills; 2: 1.66 ms, 3: 1.47 ms)
+#endif
+#ifndef MPVP_X_ZOOM_AR_STRIP
+#define MPVP_X_ZOOM_AR_STRIP 2   // member rows per strip of the anti-ringing kernel (5 accumulators per pixel: 4 rows need 148 registers)
+#endif
 constexpr int kPNT2 = kPTW * kPTH / (kStrip * kSPT);
 #ifndef MPVP_X_ZOOM_MINB
 #define MPVP_X_ZOOM_MINB 3   // resident CTAs per SM of the luma phase kernel (4 = 64 registers: measured)
 #endif
 template <int R, int C, bool AR, int SWT, bool MIX, bool TMA = false>
-__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MPVP_X_ZOOM_MINB) : 1) zoom_phase_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MPVP_X_ZOOM_MINB) : ((C == 1 && MPVP_X_ZOOM_AR_STRIP < 4) ? MPVP_X_ZOOM_AR_MINB : 1)) zoom_phase_kernel(const __grid_constant__ ZoomArgs A, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!TMA || (C == 1 && !AR && SWT > 0), "TMA staging: luma, no anti-ringing power tile, compile-time pitch");
   constexpr int kPNT = kPNT2;
   constexpr int N = 2 * R, TAPS = N * N;
   using PG = PhaseGeom<R, AR, MIX>;
   constexpr int PL = PG::PL, PITCH = PG::PITCH;
   constexpr bool POWT = AR && C == 1;   // anti-ringing powers once per staged source pixel (luma); 3-channel: on the fly
-  constexpr int STRIP = kStrip;
+  constexpr int STRIP = (AR && C == 1) ? MPVP_X_ZOOM_AR_STRIP : kStrip;
+  constexpr int SPT = kPTH / ((kPNT / kPTW) * STRIP);   // strips per thread and tile
   static_assert(!MIX || !AR, "the anti-ringing weights stay float32");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_lut = reinterpret_cast<float*>(smem_raw);            // [288][PITCH]
   float* s_src = s_lut + 288 * PITCH;                           // [C][sh][sw]
-  float4* s_pow = reinterpret_cast<float4*>(s_src + (((size_t)C * A.sh * A.sw + 3) & ~(size_t)3));   // [sh][sw] (POWT)
+  // [sh][sw] (POWT): ((0.1 + l)^32, (1.1 - l)^32) of every staged texel; the 33rd powers are one multiplication away and cost
+  // less than the second half of a 16-byte shared-memory read per tap (the tile reads are 2/3 of the kernel's wavefronts)
+  float2* s_pow = reinterpret_cast<float2*>(s_src + (((size_t)C * A.sh * A.sw + 3) & ~(size_t)3));
   __shared__ int s_mxo[kPTW], s_mxb[kPTW], s_myo[kPTH], s_myb[kPTH];
   __shared__ __align__(8) uint64_t s_mbar;
 
@@ -649,6 +661,18 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
             if (central_tap<R>(t)) d[nc++] = wv;
             else dh[nh++] = __float2half_rn(wv);
           }
+        }
+      } else if constexpr (AR) {
+        for (int i = tid; i < 288 * (TAPS / 4); i += kPNT) {
+          const int r = i / (TAPS / 4), q = i - r * (TAPS / 4);
+          const float4* __restrict__ g = reinterpret_cast<const float4*>(src + (size_t)r * PL);
+          *reinterpret_cast<float4*>(s_lut + r * PITCH + 4 * q) = __ldg(g + q);
+          const float4 a = __ldg(g + TAPS / 4 + q);
+          const __half2 h0 = __floats2half2_rn(a.x * 8192.0f, a.y * 8192.0f), h1 = __floats2half2_rn(a.z * 8192.0f, a.w * 8192.0f);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned int*>(&h0);
+          pk.y = *reinterpret_cast<const unsigned int*>(&h1);
+          *reinterpret_cast<uint2*>(s_lut + r * PITCH + TAPS + 2 * q) = pk;
         }
       } else {
         for (int i = tid; i < 288 * (PL / 4); i += kPNT) {
@@ -704,7 +728,7 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
           if constexpr (POWT) {
             const float cc = 0.1f + v, dd = 1.1f - v;
             const float pc = pow32(cc), pd = pow32(dd);
-            s_pow[d] = make_float4(pc, pd, pc * cc, pd * dd);
+            s_pow[d] = make_float2(pc, pd);
           }
         }
       }
@@ -713,7 +737,7 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
 
     const int lx = tid & (kPTW - 1);
 #pragma unroll 1
-    for (int sp = 0; sp < kSPT; ++sp) {
+    for (int sp = 0; sp < SPT; ++sp) {
     const int ly0 = (tid / kPTW + sp * (kPNT / kPTW)) * STRIP;   // this thread's member rows: ly0 .. ly0 + STRIP - 1
     if (lx >= nmx || ly0 >= nmy) continue;
     const int cnt = min(STRIP, nmy - ly0);
@@ -763,8 +787,10 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
           const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
           [[maybe_unused]] float av[4] = {0.f, 0.f, 0.f, 0.f};
           if constexpr (AR) {
-            const float4 a4 = wr[TAPS / 4 + q];
-            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            const uint2 ah = *reinterpret_cast<const uint2*>(reinterpret_cast<const float*>(wr) + TAPS + 2 * q);
+            const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&ah.x));
+            const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&ah.y));
+            av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -776,7 +802,8 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
               if constexpr (AR) {
                 float4 pw;
                 if constexpr (POWT) {
-                  pw = s_pow[(by - yb_first + t % N) * SW + (bx - xb_first) + t / N];
+                  const float2 p2 = s_pow[(by - yb_first + t % N) * SW + (bx - xb_first) + t / N];
+                  pw = make_float4(p2.x, p2.y, p2.x * (0.1f + sv), p2.y * (1.1f - sv));
                 } else {
                   const float cc = 0.1f + sv, dd = 1.1f - sv;
                   const float pc = pow32(cc), pd = pow32(dd);
@@ -852,7 +879,11 @@ struct AxisPlan {
 // members interleave irregularly).  Members of a class are cut into segments of at most `tile` members whose base
 // texels span at most tile * q + N source texels (q = the typical member distance), so a sparse class simply yields
 // shorter segments.
-AxisPlan build_axis(int O, int I, int tile, int N) {
+// exact_nodes (the anti-ringing kernels): a run of phases within fp32 noise of a LUT node (8 * sub ~ integer) is NOT merged.
+// There the sampler's blend weight of the neighbouring node is proportional to the distance from the node, the
+// anti-ringing weights feed 32nd powers, and one representative cannot stand for phases 0, 1.2e-7, 3e-5 ...: every
+// distinct value becomes a class of its own (exact 3x: 640 rows at phase 0 and eleven small classes of 1-20 rows).
+AxisPlan build_axis(int O, int I, int tile, int N, bool exact_nodes = false) {
   AxisPlan ap;
   std::vector<float> sub(O);
   std::vector<int> base(O);
@@ -862,15 +893,24 @@ AxisPlan build_axis(int O, int I, int tile, int N) {
   u.erase(std::unique(u.begin(), u.end()), u.end());
   std::vector<float> lo, hi;
   for (size_t i = 0; i < u.size(); ++i) {
-    if (i == 0 || u[i] - u[i - 1] > kClusterGap) {
+    const float u8 = 8.0f * u[i];
+    const bool at_node = exact_nodes && fabsf(u8 - rintf(u8)) < 4e-3f;
+    if (i == 0 || u[i] - u[i - 1] > kClusterGap || at_node) {
       lo.push_back(u[i]);
       hi.push_back(u[i]);
     } else {
-      hi.back() = u[i];
+      // (a phase next to a node starts a class of its own above, and the phase after it must not join that class)
+      const float p8 = 8.0f * u[i - 1];
+      if (exact_nodes && fabsf(p8 - rintf(p8)) < 4e-3f) {
+        lo.push_back(u[i]);
+        hi.push_back(u[i]);
+      } else {
+        hi.back() = u[i];
+      }
     }
   }
   const int ncls = (int)lo.size();
-  if (ncls > kMaxClasses) return ap;
+  if (ncls > (exact_nodes ? kMaxClassesExact : kMaxClasses)) return ap;
   for (int c = 0; c < ncls; ++c)
     if (hi[c] - lo[c] > kMaxSpread) return ap;
   ap.off.assign(ncls + 1, 0);
@@ -985,20 +1025,23 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
   z->h = h; z->w = w; z->oh = oh; z->ow = ow; z->lut_ar = lut_ar;
   cache->plans.push_back(z);
   constexpr int N = 2 * R;
-  const AxisPlan ax = build_axis(ow, w, kPTW, N), ay = build_axis(oh, h, kPTH, N);
+  const AxisPlan ax = build_axis(ow, w, kPTW, N, AR), ay = build_axis(oh, h, kPTH, N, AR);
   if (env_flag("MPVP_DEBUG_ZOOM", false))
     fprintf(stderr, "[mpvp] zoom plan %dx%d -> %dx%d: x %s (%zu classes, %zu segments, need %d), y %s (%zu classes, %zu segments, need %d)\n",
             w, h, ow, oh, ax.ok ? "ok" : "no", ax.rep.size(), ax.seg.size(), ax.max_need, ay.ok ? "ok" : "no", ay.rep.size(),
             ay.seg.size(), ay.max_need);
   if (!ax.ok || !ay.ok) return nullptr;
-  if (AR && (ax.node_spread || ay.node_spread)) return nullptr;
+#ifndef MPVP_X_ZOOM_AR_SPREAD_OK
+#define MPVP_X_ZOOM_AR_SPREAD_OK 0   // timing experiments only: wrong results on the rows / columns whose phase scatters around a node
+#endif
+  if (AR && (ax.node_spread || ay.node_spread) && !MPVP_X_ZOOM_AR_SPREAD_OK) return nullptr;
   const int ncx = (int)ax.rep.size(), ncy = (int)ay.rep.size();
   z->ncp = ncx * ncy;
   z->sw = ax.max_need | 1;   // odd pitch: member windows one or more texels apart spread over the banks
   z->sh = ay.max_need;
   constexpr int PL = PhaseGeom<R, AR, false>::PL;
   const size_t smem = sizeof(float) * (288 * PhaseGeom<R, AR, false>::PITCH + (((size_t)C * z->sw * z->sh + 3) & ~(size_t)3)) +
-                      ((AR && C == 1) ? sizeof(float4) * (size_t)z->sw * z->sh : 0);
+                      ((AR && C == 1) ? sizeof(float2) * (size_t)z->sw * z->sh : 0);
   if (smem > 200 * 1024) return nullptr;
   int start = 0;
   for (int cy = 0; cy < ncy; ++cy)
@@ -1100,7 +1143,7 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
       ptma = fixed_pitch && a.io.in_fmt == MPVP_FMT_F32 && make_plane_tmap(&ptm, a.in, 4, a.w, a.h, a.n, a.in_sy, a.in_sn, kSWT, a.sh);
     auto launch = [&](auto kern, int pitch) {
       const size_t smem = sizeof(float) * (288 * (size_t)pitch + (((size_t)C * a.sw * a.sh + 3) & ~(size_t)3)) +
-                          ((AR && C == 1) ? sizeof(float4) * (size_t)a.sw * a.sh : 0);
+                          ((AR && C == 1) ? sizeof(float2) * (size_t)a.sw * a.sh : 0);
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       int per_sm = 0;
       if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPNT2, smem);

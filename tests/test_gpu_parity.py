@@ -285,6 +285,13 @@ def test_config4_zoom_ar_r2_720p_crop():
     _run_ravu_variant("ravu-zoom-ar-r2.hook", n=1, h=360, w=640, config=4, out_hw=(1080, 1920))
 
 
+def test_config4_zoom_ar_r2_full_720p_to_2160p():
+    """The anti-ringing half of configs[3] at full size: at exact 3x the 720-row axis has 640 rows at phase 0 and eleven small
+    classes a few float32 ulps off the LUT node, which the phase path keeps apart: the 32nd powers of the
+    soft min / max turn a merged class into errors of 5e-3."""
+    _run_ravu_variant("ravu-zoom-ar-r2.hook", n=1, h=720, w=1280, config=4, out_hw=(2160, 3840))
+
+
 def test_ravu_3x_r3_full_720p_frame():
     _run_ravu_variant("compute/ravu-3x-r3.hook", n=1, h=720, w=1280, config=6)
 
