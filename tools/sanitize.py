@@ -25,6 +25,8 @@ cases = [
     ("ravu-zoom-r3.hook", (2, 40, 60), (120, 180), {}),        # exact 3x: key pre-pass + phase kernel (TMA)
     ("ravu-zoom-r2.hook", (1, 41, 61), (82, 122), {}),         # exact 2x: phase kernel, plain staging
     ("ravu-zoom-ar-r2-rgb.hook", (1, 3, 40, 60), (120, 180), {}),
+    ("ravu-zoom-ar-r2.hook", (2, 120, 90), (360, 270), {}),    # exact 3x, anti-ringing: phase kernel with exact node classes
+    ("ravu-zoom-ar-r2.hook", (1, 50, 70), (100, 140), {}),     # exact 2x, anti-ringing phase kernel
     ("nnedi3-nns256-win8x6.hook", (1, 40, 70), None, {}),
     ("nnedi3-nns32-win8x4.hook", (2, 40, 70), None, {}),
     ("nnedi3-nns64-win8x6.hook", (1, 40, 70), None, {}),
