@@ -909,21 +909,37 @@ AxisPlan build_axis(int O, int I, int tile, int N, bool exact_nodes = false) {
   u.erase(std::unique(u.begin(), u.end()), u.end());
   std::vector<float> lo, hi;
   for (size_t i = 0; i < u.size(); ++i) {
-    const float u8 = 8.0f * u[i];
-    const bool at_node = exact_nodes && fabsf(u8 - rintf(u8)) < 4e-3f;
-    if (i == 0 || u[i] - u[i - 1] > kClusterGap || at_node) {
+    if (i == 0 || u[i] - u[i - 1] > kClusterGap) {
       lo.push_back(u[i]);
       hi.push_back(u[i]);
     } else {
-      // (a phase next to a node starts a class of its own above, and the phase after it must not join that class)
-      const float p8 = 8.0f * u[i - 1];
-      if (exact_nodes && fabsf(p8 - rintf(p8)) < 4e-3f) {
-        lo.push_back(u[i]);
-        hi.push_back(u[i]);
+      hi.back() = u[i];
+    }
+  }
+  if (exact_nodes) {
+    // The blend weight of the FARTHER node is 8 * (distance of the phase to the nearer node): a class whose spread is not
+    // small against that distance (on a node the distance is 0) cannot be represented by one phase when the weights feed
+    // 32nd powers -- a relative error e of one weight moves the soft min / max by up to e / 4 of the local contrast.
+    // Such a class is dissolved into its distinct values (spread <= 4e-3 of the distance keeps the shift below 1e-3).
+    std::vector<float> lo2, hi2;
+    for (size_t c = 0; c < lo.size(); ++c) {
+      const float mid = 0.5f * (lo[c] + hi[c]);
+      const float node = rintf(8.0f * mid) / 8.0f;
+      const float dist = fminf(fabsf(lo[c] - node), fabsf(hi[c] - node));
+      const bool straddles = lo[c] <= node && node <= hi[c];
+      if (lo[c] != hi[c] && (straddles || hi[c] - lo[c] > 4e-3f * dist)) {
+        for (float v : u)
+          if (v >= lo[c] && v <= hi[c]) {
+            lo2.push_back(v);
+            hi2.push_back(v);
+          }
       } else {
-        hi.back() = u[i];
+        lo2.push_back(lo[c]);
+        hi2.push_back(hi[c]);
       }
     }
+    lo.swap(lo2);
+    hi.swap(hi2);
   }
   const int ncls = (int)lo.size();
   if (ncls > (exact_nodes ? kMaxClassesExact : kMaxClasses)) return ap;
