@@ -132,11 +132,36 @@ __global__ void __launch_bounds__(kRNT) resample_kernel(const __grid_constant__ 
       };
       const int64_t o0 = (int64_t)p * A.out_sp + (int64_t)oy0 * A.out_sy + ox0 + lx;
       if (F32 && nx == kRTW && ny == TH && A.out_sy < (1 << 24)) {
-        // full tile, float32 out: no predicates, 32-bit row offsets
+        // full tile, float32 out: no predicates, 32-bit row offsets.  The thread takes TH / RG CONSECUTIVE rows and keeps its
+        // T filtered-row values in registers: when the base of the next row is the same or one further (every ratio >= 1),
+        // the window slides by at most one shared-memory read instead of T (the test is warp-uniform: a warp shares ly)
         float* __restrict__ q = static_cast<float*>(A.out) + o0;
         const int pitch = (int)A.out_sy;
+        constexpr int RPT = TH / RG;
+        float win[T];
+        int wb = -(1 << 20);
 #pragma unroll 4
-        for (int j = 0; j < TH / RG; ++j) column(ty + j * RG, [&](int ly, float v) { __stcs(q + ly * pitch, v); });
+        for (int j = 0; j < RPT; ++j) {
+          const int ly = ty * RPT + j;
+          const int b = s_by[ly] - y_lo;
+          const float* __restrict__ c = s_row + b * kRTW + lx;
+          if (T >= 4 && b == wb + 1) {                  // (two taps: sliding costs what it saves)
+#pragma unroll
+            for (int k = 0; k + 1 < T; ++k) win[k] = win[k + 1];
+            win[T - 1] = c[(T - 1) * kRTW];
+          } else if (T < 4 || b != wb) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) win[k] = c[k * kRTW];
+          }
+          wb = b;
+          float wy[8];
+          *reinterpret_cast<float4*>(wy) = *reinterpret_cast<const float4*>(&s_wy[ly][0]);
+          if (T > 4) *reinterpret_cast<float2*>(wy + 4) = *reinterpret_cast<const float2*>(&s_wy[ly][4]);
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < T; ++k) acc = fmaf(win[k], wy[k], acc);
+          __stcs(q + ly * pitch, acc);
+        }
       } else if (lx < nx) {
         for (int ly = ty; ly < ny; ly += RG)
           column(ly, [&](int l, float v) { store_px(A.out, o0 + (int64_t)l * A.out_sy, v, A.io.out_fmt, A.io.out_max); });
