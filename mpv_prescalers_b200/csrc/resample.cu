@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpvp {
 namespace {
@@ -39,6 +40,7 @@ struct ResampleArgs {
   const int* __restrict__ by; const float* __restrict__ wy;   // [oh], [oh][taps]
   int planes, h, w, oh, ow, taps;
   int sw, sh;   // shared source tile: pitch and rows
+  int tma_w;    // TMA variant: box width = pitch
   int64_t in_sp, in_sy, out_sp, out_sy;
   int tiles_x, tiles_y;
   long long total_tiles;
@@ -52,7 +54,7 @@ struct ResampleArgs {
 // element -- spent 160 warp instructions per 32 pixels, 70 % issue-bound at 14 % of the HBM roofline.)
 template <int T, int SWT, bool F32, int TH>
 __global__ void __launch_bounds__(kRNT) resample_kernel(const __grid_constant__ ResampleArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_src = reinterpret_cast<float*>(smem_raw);   // [sh][SWT]
   float* s_row = s_src + A.sh * SWT;                   // [sh][kRTW]: horizontally filtered rows
   __shared__ int s_by[TH];
@@ -165,6 +167,115 @@ __global__ void __launch_bounds__(kRNT) resample_kernel(const __grid_constant__ 
       } else if (lx < nx) {
         for (int ly = ty; ly < ny; ly += RG)
           column(ly, [&](int l, float v) { store_px(A.out, o0 + (int64_t)l * A.out_sy, v, A.io.out_fmt, A.io.out_max); });
+      }
+    }
+  }
+}
+
+// float32 planes, no reduction (ratio >= 1 on both axes), TMA-legal layout: the source tile arrives by cp.async.bulk.tensor
+// into one of two staging buffers -- the box starts at the 16-byte aligned texel at or left of the tile's first texel and
+// is PW texels wide; out-of-image texels arrive as zeros and border tiles are patched to clamp-to-edge -- while the
+// previous tile is filtered: no staging instructions, no global loads in the filters.  Two barriers per tile.
+constexpr int kTmaWMax = 76;   // box width <= 73 + 3 texels of slack for the aligned origin, a multiple of 4 texels
+template <int T, int TH, int PW>
+__global__ void __launch_bounds__(kRNT) resample_tma_kernel(const __grid_constant__ ResampleArgs A, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // PW: box width = pitch of the staged tile, compile-time (76 for ratios near 1, 44 from 2x up)
+  const int BUF = (A.sh * PW + 31) & ~31;               // floats per staging buffer (128-byte multiple)
+  float* s_src = reinterpret_cast<float*>(smem_raw);   // [2][sh][PW]
+  float* s_row = s_src + 2 * BUF;                      // [sh][kRTW]
+  __shared__ int s_by2[2][TH];
+  __shared__ __align__(16) float s_wy2[2][TH][8];
+  __shared__ __align__(8) uint64_t s_mbar[2];
+  const int tid = threadIdx.x;
+  const int lx = tid & (kRTW - 1), ty = tid / kRTW;
+  constexpr int RG = kRNT / kRTW, RPT = TH / RG;
+  if (tid == 0) {
+    mbar_init1(smem_addr(&s_mbar[0]));
+    mbar_init1(smem_addr(&s_mbar[1]));
+    mbar_init_fence();
+  }
+  __syncthreads();
+  const uint64_t tmap_ptr = reinterpret_cast<uint64_t>(&tmap);
+  auto issue = [&](const TileWalk& w, int buf) {     // one elected thread of warp 0
+    const int x_lo = __ldg(A.bx + w.tix * kRTW), y_lo = __ldg(A.by + w.tiy * TH);
+    const uint32_t bar = smem_addr(&s_mbar[buf]);
+    tma_expect(bar, (uint32_t)(PW * A.sh * 4));
+    tma_load_3d(smem_addr(s_src + buf * BUF), tmap_ptr, x_lo & ~3, y_lo, w.f, bar);
+  };
+  TileWalk walk(blockIdx.x, gridDim.x, A.tiles_x, A.tiles_y);
+  TileWalk ahead = walk;
+  if (tid < 32 && blockIdx.x < A.total_tiles) {
+    if (elect_one()) issue(ahead, 0);
+  }
+  ahead.next();
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, walk.next(), ahead.next(), ++it) {
+    const int ox0 = walk.tix * kRTW, oy0 = walk.tiy * TH, p = walk.f;
+    const int nx = min(kRTW, A.ow - ox0), ny = min(TH, A.oh - oy0);
+    const int oxc = ox0 + min(lx, nx - 1);
+    const int bxc = __ldg(A.bx + oxc);
+    float wxr[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) wxr[k] = __ldg(A.wx + (size_t)oxc * T + k);
+    const int x_lo = __ldg(A.bx + ox0), y_lo = __ldg(A.by + oy0);
+    const int need_h = __ldg(A.by + oy0 + ny - 1) + T - y_lo;
+    const int ax0 = x_lo & ~3;
+    int* __restrict__ s_by = s_by2[it & 1];
+    float (*__restrict__ s_wy)[8] = s_wy2[it & 1];
+    if (tid < TH) {
+      const int o = oy0 + min(tid, ny - 1);
+      s_by[tid] = __ldg(A.by + o);
+#pragma unroll
+      for (int k = 0; k < T; ++k) s_wy[tid][k] = __ldg(A.wy + (size_t)o * T + k);
+    }
+    __syncthreads();   // the column filter of the previous tile is done with s_row; the other staging buffer is free
+    if (tid < 32 && tile + gridDim.x < A.total_tiles) {
+      fence_proxy_async_smem();
+      if (elect_one()) issue(ahead, (it + 1) & 1);
+    }
+    float* __restrict__ buf = s_src + (it & 1) * BUF;
+    mbar_wait_parity(smem_addr(&s_mbar[it & 1]), (it >> 1) & 1);
+    const bool edge = ax0 < 0 || y_lo < 0 || ax0 + PW > A.w || y_lo + A.sh > A.h;
+    if (edge) patch_clamp_to_edge(buf, PW, PW, A.sh, ax0, y_lo, A.w, A.h, tid, kRNT, [] { __syncthreads(); });
+    {
+      const float* __restrict__ r = buf + ty * PW + (bxc - ax0);
+      float* __restrict__ d = s_row + ty * kRTW + lx;
+#pragma unroll 2
+      for (int sy = ty; sy < need_h; sy += RG, r += RG * PW, d += RG * kRTW) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < T; ++k) acc = fmaf(r[k], wxr[k], acc);
+        *d = acc;
+      }
+    }
+    __syncthreads();
+    float* __restrict__ q = static_cast<float*>(A.out) + (int64_t)p * A.out_sp + (int64_t)oy0 * A.out_sy + ox0 + lx;
+    if (lx < nx) {
+      float win[T];
+      int wb = -(1 << 20);
+#pragma unroll 4
+      for (int j = 0; j < RPT; ++j) {
+        const int ly = ty * RPT + j;
+        if (ly >= ny) break;
+        const int b = s_by[ly] - y_lo;
+        const float* __restrict__ c = s_row + b * kRTW + lx;
+        if (T >= 4 && b == wb + 1) {
+#pragma unroll
+          for (int k = 0; k + 1 < T; ++k) win[k] = win[k + 1];
+          win[T - 1] = c[(T - 1) * kRTW];
+        } else if (T < 4 || b != wb) {
+#pragma unroll
+          for (int k = 0; k < T; ++k) win[k] = c[k * kRTW];
+        }
+        wb = b;
+        const float4 w03 = *reinterpret_cast<const float4*>(&s_wy[ly][0]);
+        const float2 w45 = *reinterpret_cast<const float2*>(&s_wy[ly][4]);
+        const float wy[6] = {w03.x, w03.y, w03.z, w03.w, w45.x, w45.y};
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < T; ++k) acc = fmaf(win[k], wy[k], acc);
+        __stcs(q + (int64_t)ly * A.out_sy, acc);
       }
     }
   }
@@ -315,6 +426,33 @@ extern "C" int mpvp_resample_launch_io(int device, int kernel, const void* in, v
   };
   auto kern = a.taps == 2 ? pick(std::integral_constant<int, 2>{})
               : (a.taps == 4 ? pick(std::integral_constant<int, 4>{}) : pick(std::integral_constant<int, 6>{}));
+  // TMA-staged variant: float32 planes, no reduction (th == 64, staged width <= 73), layout within TMA's 16-byte rules
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  a.tma_w = (ax.need + 3 + 3) & ~3;     // staged extent + up to 3 texels left of it (aligned origin), a multiple of 4
+  a.tma_w = a.tma_w <= 44 ? 44 : kTmaWMax;
+  if (f32 && th == 64 && ax.need + 3 <= kTmaWMax && a.sh <= 256 &&
+      make_plane_tmap(&tmap, in, 4, w, h, planes, in_stride_y, in_stride_p, a.tma_w, a.sh)) {
+    auto tpick = [&](auto tag) {
+      constexpr int T = decltype(tag)::value;
+      return a.tma_w == 44 ? resample_tma_kernel<T, 64, 44> : resample_tma_kernel<T, 64, kTmaWMax>;
+    };
+    auto tk = a.taps == 2 ? tpick(std::integral_constant<int, 2>{})
+              : (a.taps == 4 ? tpick(std::integral_constant<int, 4>{}) : tpick(std::integral_constant<int, 6>{}));
+    const size_t tsm = sizeof(float) * (2 * (size_t)((a.sh * a.tma_w + 31) & ~31) + (size_t)a.sh * kRTW) + 128;
+    MPVP_CUDA_OK(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    int per = 0;
+    MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, tk, kRNT, tsm));
+    if (per >= 1) {
+      long long grid = (long long)sm_count(device) * per;
+      if (grid > a.total_tiles) grid = a.total_tiles;
+      grid = cap_grid(grid);
+      tk<<<(unsigned)grid, kRNT, tsm, static_cast<cudaStream_t>(stream)>>>(a, tmap);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      MPVP_CUDA_OK(cudaGetLastError());
+      return MPVP_OK;
+    }
+  }
   MPVP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MPVP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRNT, smem));
