@@ -70,6 +70,7 @@ struct ZoomArgs {
   const ClassPair* __restrict__ cps;
   int ncp;
   int tiles_per_frame, fgroup;      // member tiles of one frame (all class pairs); frames per L2-resident group
+  const long long* __restrict__ cta_begin;   // [grid + 1] first work item of every CTA (cost-balanced), or null
   const float* __restrict__ plut;   // [ncp][288][PL]
   unsigned short* __restrict__ kmap;  // [n][h + 1][w + 1] LUT row of the source cell with base texel (x - 1, y - 1)
   int sw, sh;                       // staged source rectangle (pitch, rows) the plan needs
@@ -393,6 +394,10 @@ int launch_zoom_impl(const ZoomArgs& a0, int device, cudaStream_t stream) {
   return MPVP_OK;
 }
 
+long long env_int(const char* name, long long dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoll(e) : dflt;
+}
 bool env_flag(const char* name, bool dflt) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
@@ -631,7 +636,10 @@ __global__ void __launch_bounds__(kPNT2, (C == 1 && !AR) ? (kStrip <= 2 ? 2 : MP
   const int cw = A.w + 1, ch = A.h + 1;
   // contiguous run of work items (class-pair major): at most a couple of phase-LUT reloads per CTA
   const long long T = A.total_tiles;
-  const long long w_begin = T * blockIdx.x / gridDim.x, w_end = T * (blockIdx.x + 1) / gridDim.x;
+  // member tiles differ in cost (partial segments, the small exact classes of the anti-ringing plans): the host cuts the
+  // item list into ranges of equal estimated cost instead of equal length
+  const long long w_begin = A.cta_begin ? A.cta_begin[blockIdx.x] : T * blockIdx.x / gridDim.x;
+  const long long w_end = A.cta_begin ? A.cta_begin[blockIdx.x + 1] : T * (blockIdx.x + 1) / gridDim.x;
   // Frames are taken in GROUPS whose output stays in L2 (A.fgroup frames): the class pairs of a geometry each write every
   // P-th pixel of a row, i.e. a fraction of every 32-byte sector, and with all frames of a class pair done before the next
   // pair starts the partially written sectors are evicted and re-fetched once per class pair.  Measured (ncu, zoom-r3,
@@ -1009,6 +1017,10 @@ struct ZoomPlan {
   // key-map scratch of the pre-pass, owned by the plan and grown on demand: launches allocate nothing in the steady
   // state (a stream-ordered cudaMallocAsync would be re-allocated after every synchronisation of the caller: the
   // default pool trims to zero).  `kmap_ev` orders a launch after the previous user of the buffer, whatever its stream.
+  // cost model of the work items (one prefix array per class pair over its tiles of ONE frame) and the cached CTA ranges
+  std::vector<std::vector<long long>> cp_prefix;
+  struct Ranges { int n, grid, fgroup; long long* dev; };
+  std::vector<Ranges> ranges;
   std::mutex kmu;
   unsigned short* kmap = nullptr;
   size_t kmap_cap = 0;
@@ -1017,6 +1029,7 @@ struct ZoomPlan {
     cudaFree(xo); cudaFree(xb); cudaFree(yo); cudaFree(yb); cudaFree(xseg); cudaFree(yseg); cudaFree(cps); cudaFree(plut);
     if (kmap_ev) { cudaEventSynchronize(kmap_ev); cudaEventDestroy(kmap_ev); }
     cudaFree(kmap);
+    for (auto& r : ranges) cudaFree(r.dev);
   }
 };
 struct ZoomPlanCache {
@@ -1086,6 +1099,20 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
       z->cps_host.push_back(cp);
     }
   z->total_tiles_per_frame = start;
+  {
+    // estimated cost of a member tile: a fixed part (staging, barriers, table loads, in units of one pixel) + its pixels.
+    // Measured (config 4, 8 frames; equal-length ranges 0.874 / 1.660 ms for r3 / ar-r2): fixed = 128: 1.32 / 2.14, 384:
+    // 1.08 / 1.86, 768: 0.92 / 1.60, 1536: 0.851 / 1.471, 2048: 0.848 / 1.498, 4096: 0.855 / 1.549 -- the set-up of a
+    // tile costs about as much as the pixels of a full 64 x 32 tile.
+    const long long fixed = env_int("MPVP_ZOOM_COST_FIXED", AR ? 1536 : 2048);
+    for (const ClassPair& cp : z->cps_host) {
+      std::vector<long long> pre(1, 0);
+      for (int ty = 0; ty < cp.tiles_y; ++ty)
+        for (int tx = 0; tx < cp.tiles_x; ++tx)
+          pre.push_back(pre.back() + fixed + (long long)ax.seg[cp.xsoff + tx].y * ay.seg[cp.ysoff + ty].y);
+      z->cp_prefix.push_back(std::move(pre));
+    }
+  }
   float *rep_x = nullptr, *rep_y = nullptr;
   cudaError_t e = upload(z->xo, ax.o);
   if (e == cudaSuccess) e = upload(z->xb, ax.b);
@@ -1114,6 +1141,47 @@ ZoomPlan* get_plan(const mpvp_weights* lut, const mpvp_weights* lut_ar, int h, i
   }
   z->usable = true;
   return z;
+}
+
+// First work item of every CTA for an n-frame launch on `grid` CTAs: ranges of equal estimated cost.  The item order is
+// (group of fgroup frames, class pair, frame, tile); the cost of an item depends on (class pair, tile) only, so the item at a
+// given cumulative cost is found by division and one binary search.  Cached per (n, grid, fgroup) on the plan (caller holds
+// z->kmu); null if the device allocation fails (the kernel then falls back to ranges of equal length).
+const long long* cta_ranges(ZoomPlan* z, int n, int grid, int fgroup) {
+  for (const auto& r : z->ranges)
+    if (r.n == n && r.grid == grid && r.fgroup == fgroup) return r.dev;
+  const int ncp = (int)z->cps_host.size();
+  long long frame_cost = 0;
+  for (const auto& pre : z->cp_prefix) frame_cost += pre.back();
+  const long long tpf = z->total_tiles_per_frame;
+  const long long total_cost = frame_cost * n, total_items = tpf * n;
+  const int ngroups = (n + fgroup - 1) / fgroup;
+  std::vector<long long> b((size_t)grid + 1);
+  for (int k = 0; k <= grid; ++k) {
+    if (k == grid) { b[k] = total_items; break; }
+    long long t = total_cost / grid * k + total_cost % grid * k / grid;      // = floor(total_cost * k / grid) without overflow
+    int g = (int)std::min<long long>(t / (frame_cost * fgroup), ngroups - 1);
+    t -= (long long)g * frame_cost * fgroup;
+    const int gn = std::min(fgroup, n - g * fgroup);
+    int cp = 0;
+    while (cp + 1 < ncp && t >= z->cp_prefix[cp].back() * gn) { t -= z->cp_prefix[cp].back() * gn; ++cp; }
+    const auto& pre = z->cp_prefix[cp];
+    const long long f = std::min<long long>(t / pre.back(), gn - 1);
+    t -= f * pre.back();
+    const long long tl = std::min<long long>((long long)(std::upper_bound(pre.begin(), pre.end(), t) - pre.begin()) - 1, (long long)pre.size() - 2);
+    b[k] = (long long)g * fgroup * tpf + (long long)z->cps_host[cp].tile_start * gn + f * ((long long)pre.size() - 1) + std::max<long long>(tl, 0);
+  }
+  for (int k = 1; k <= grid; ++k) b[k] = std::max(b[k], b[k - 1]);
+  long long* dev = nullptr;
+  if (cudaMalloc(&dev, b.size() * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (cudaMemcpy(dev, b.data(), b.size() * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(dev);
+    return nullptr;
+  }
+  if (z->ranges.size() >= 16) { cudaFree(z->ranges.front().dev); z->ranges.erase(z->ranges.begin()); }   // (launches are ordered by kmap_ev)
+  z->ranges.push_back({n, grid, fgroup, dev});
+  return dev;
 }
 
 template <int R, int C, int KEYMODE, bool AR>
@@ -1196,6 +1264,7 @@ int launch_zoom_phase(ZoomArgs a, ZoomPlan* z, int device, cudaStream_t stream) 
       long long grid = (long long)sm_count(device) * per_sm;
       if (grid > total) grid = total;
       grid = cap_grid(grid);
+      a.cta_begin = env_flag("MPVP_ZOOM_BALANCE", true) ? cta_ranges(z, a.n, (int)grid, a.fgroup) : nullptr;
       kern<<<(unsigned)grid, kPNT2, smem, stream>>>(a, ptm);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     };
