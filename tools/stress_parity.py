@@ -2,7 +2,7 @@
 """Randomised parity sweep (not part of the test suite: minutes of GPU + oracle time): many seeded plane sizes, batch sizes
 and ratios per family, each compared with the oracle by the same helpers the GPU tests use.
 
-    python tools/stress_parity.py [cases_per_family] [seed]
+    python tools/stress_parity.py [cases_per_family] [seed] [max_h max_w]
 """
 import os
 import sys
@@ -27,10 +27,11 @@ NN = ["nnedi3-nns16-win8x4.hook", "nnedi3-nns32-win8x6.hook", "nnedi3-nns64-win8
 def main():
     per = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    hmax, wmax = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (200, 330)
     rng = np.random.default_rng(seed)
     fails, runs, t0 = [], 0, time.time()
     for name in RAVU:
-        for h, w in T._random_sizes(int(rng.integers(1 << 30)), per, 200, 330):
+        for h, w in T._random_sizes(int(rng.integers(1 << 30)), per, hmax, wmax):
             n = int(rng.integers(1, 4))
             out_hw = None
             if "zoom" in name:
@@ -57,7 +58,7 @@ def main():
 
     for name in NN:
         hk = HookFile.parse(hook_path(name))
-        for h, w in T._random_sizes(int(rng.integers(1 << 30)), max(2, per // 2), 90, 220):
+        for h, w in T._random_sizes(int(rng.integers(1 << 30)), max(2, per // 2), max(90, hmax // 2), max(220, wmax // 2)):
             n = int(rng.integers(1, 3))
             x = batch(n, 1, h, w, config=int(rng.integers(100, 900)))
             cap = int(rng.integers(1, 4)) if rng.random() < 0.3 else 0
